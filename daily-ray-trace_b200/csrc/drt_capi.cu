@@ -1,0 +1,411 @@
+/*
+ * csrc/drt_capi.cu -- the C ABI of include/drt_cuda.h over the kernels in this directory.
+ *
+ * Host-side work here is only: narrowing the f64 scene into the device layout (precomputing what the reference
+ * recomputes per call, e.g. the normalised plane frame of line_plane_intersection, geometry.c:166-170), owning
+ * device buffers, sizing the persistent grid, and launching.  There is no CPU implementation of any render step.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "drt_cuda.h"
+#include "drt_device.cuh"
+
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
+size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps);
+void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
+                                   float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
+void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
+void        drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream_t stream);
+size_t      drt_rgb_tables_bytes(void);
+void        drt_fill_rgb_tables(void *dst_host, const drt_tables *t);
+
+static thread_local char g_err[512];
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while(0)
+
+struct drt_cuda_context
+{
+    int    device = 0;
+    int    num_sms = 0;
+    size_t smem_optin = 0;
+    bool   have_scene = false;
+    bool   f64_geometry = false;
+    int    n = 0, nslots = 0, nlights = 0;
+    void  *d_geom32 = nullptr, *d_geom64 = nullptr;
+    SpdIndex *d_index = nullptr;
+    float *d_pool = nullptr;
+    uint32_t pool_words = 0;
+    void  *d_rgb_tables = nullptr;
+    DeviceStats *d_stats = nullptr;
+    unsigned int *d_counter = nullptr;
+    /* library-owned film + dump buffers for the host-buffer entry points */
+    float *d_film = nullptr; size_t film_bytes = 0;
+    float *d_dump = nullptr; size_t dump_bytes = 0;
+    uint64_t launches = 0;
+    uint64_t last_launches = 0;
+};
+
+extern "C" const char *drt_cuda_last_error(void) { return g_err; }
+
+extern "C" int drt_cuda_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int drt_cuda_create(int device, drt_cuda_context **out)
+{
+    if(!out) return fail(DRT_CUDA_E_ARG, "out is NULL");
+    int count = drt_cuda_device_count();
+    if(count <= 0) return fail(DRT_CUDA_E_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+    if(device < 0 || device >= count) return fail(DRT_CUDA_E_ARG, "device %d out of range (%d visible)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    drt_cuda_context *ctx = new drt_cuda_context();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaMalloc(&ctx->d_stats, sizeof(DeviceStats)));
+    CU(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+    *out = ctx;
+    return DRT_CUDA_OK;
+}
+
+extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
+{
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
+    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats); cudaFree(ctx->d_counter); cudaFree(ctx->d_film); cudaFree(ctx->d_dump);
+    delete ctx;
+}
+
+/* value_at_wl, spectrum.c:150-162, in f64 on the host */
+static double value_at_wl(const drt_scene *s, const double *spd, double wl)
+{
+    uint32_t i0 = (uint32_t)((wl - s->min_wl) / s->wl_interval), i1 = i0 + 1;
+    double w0 = s->min_wl + i0 * s->wl_interval, w1 = s->min_wl + i1 * s->wl_interval;
+    return spd[i0] + ((wl - w0) * ((spd[i1] - spd[i0]) / (w1 - w0)));
+}
+
+template <typename R>
+static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
+{
+    memset(g, 0, sizeof(*g));
+    g->nsurf = s->num_surfaces; g->nmat = s->num_materials; g->n = s->num_wavelengths;
+    g->base_mat = s->base_material; g->escape_mat = s->escape_material;
+    uint32_t i0 = (uint32_t)((DRT_TRANS_WL - s->min_wl) / s->wl_interval);
+    double w0 = s->min_wl + i0 * s->wl_interval, w1 = s->min_wl + (i0 + 1) * s->wl_interval;
+    g->trans_num = (R)(DRT_TRANS_WL - w0);
+    g->trans_den = (R)(w1 - w0);
+    int nl = 0;
+    for(int i = 0; i < s->num_surfaces; i += 1)
+    {
+        const drt_surface *f = &s->surfaces[i];
+        g->type[i] = f->type; g->mat[i] = f->material;
+        g->px[i] = (R)f->position[0]; g->py[i] = (R)f->position[1]; g->pz[i] = (R)f->position[2];
+        g->rad[i] = (R)f->radius;
+        g->nx[i] = (R)f->normal[0]; g->ny[i] = (R)f->normal[1]; g->nz[i] = (R)f->normal[2];
+        g->ux[i] = (R)f->u[0]; g->uy[i] = (R)f->u[1]; g->uz[i] = (R)f->u[2];
+        g->vx[i] = (R)f->v[0]; g->vy[i] = (R)f->v[1]; g->vz[i] = (R)f->v[2];
+        double pdf = 1.0;
+        if(f->type == DRT_GEO_PLANE)
+        {
+            double ul = sqrt(f->u[0] * f->u[0] + f->u[1] * f->u[1] + f->u[2] * f->u[2]);
+            double vl = sqrt(f->v[0] * f->v[0] + f->v[1] * f->v[1] + f->v[2] * f->v[2]);
+            g->ulen[i] = (R)ul; g->vlen[i] = (R)vl;
+            g->unx[i] = (R)(f->u[0] / ul); g->uny[i] = (R)(f->u[1] / ul); g->unz[i] = (R)(f->u[2] / ul);
+            g->vnx[i] = (R)(f->v[0] / vl); g->vny[i] = (R)(f->v[1] / vl); g->vnz[i] = (R)(f->v[2] / vl);
+            double cx = f->u[1] * f->v[2] - f->u[2] * f->v[1], cy = f->u[2] * f->v[0] - f->u[0] * f->v[2], cz = f->u[0] * f->v[1] - f->u[1] * f->v[0];
+            pdf = sqrt(cx * cx + cy * cy + cz * cz);                       /* daily_ray_trace.c:314 */
+        }
+        else if(f->type == DRT_GEO_SPHERE) pdf = (double)(4.0 * 3.1415926535897932385L * f->radius * f->radius);   /* :304 */
+        g->light_pdf[i] = (R)pdf;
+        if(s->materials[f->material].is_emissive) g->light_surf[nl++] = i;
+    }
+    g->nlights = nl;
+    for(int m = 0; m < s->num_materials; m += 1)
+    {
+        const drt_material *mm = &s->materials[m];
+        g->mflags[m] = (mm->is_black_body ? 1 : 0) | (mm->is_emissive ? 2 : 0);
+        g->nlobes[m] = mm->num_lobes; g->dirf[m] = mm->dir_func;
+        for(int k = 0; k < mm->num_lobes && k < DRT_MAX_LOBES; k += 1) g->lobes[m][k] = (unsigned char)mm->lobes[k];
+        g->shin[m] = (R)mm->shininess; g->rough[m] = (R)mm->roughness;
+        if(mm->spd_mask & (1 << DRT_SPD_REFRACT))
+        {
+            g->n630[m] = (R)value_at_wl(s, mm->spd[DRT_SPD_REFRACT], DRT_TRANS_WL);
+            g->refr_a[m] = (R)mm->spd[DRT_SPD_REFRACT][i0];
+            g->refr_b[m] = (R)mm->spd[DRT_SPD_REFRACT][i0 + 1];
+        }
+    }
+    for(int k = 0; k < 3; k += 1)
+    {
+        g->fwd[k] = (R)c->forward[k]; g->right[k] = (R)c->right[k]; g->up[k] = (R)c->up[k];
+        g->ap_pos[k] = (R)c->aperture_position[k]; g->film_bl[k] = (R)c->film_bottom_left[k];
+    }
+    g->ap_radius = (R)c->aperture_radius; g->focal_depth = (R)c->focal_depth;
+    g->pixel_w = (R)c->pixel_width; g->pixel_h = (R)c->pixel_height;
+    for(int k = 0; k < 9; k += 1) g->lens_rot[k] = (R)c->lens_rotation[k];
+}
+
+extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables)
+{
+    if(!ctx || !scene || !camera || !tables) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    int n = scene->num_wavelengths;
+    if(n < 2 || n > DRT_MAX_WAVELENGTHS) return fail(DRT_CUDA_E_ARG, "%d wavelengths (need 2..%d)", n, DRT_MAX_WAVELENGTHS);
+    if(scene->num_surfaces < 0 || scene->num_surfaces > DRT_MAX_SURFACES || scene->num_materials < 1 || scene->num_materials > DRT_MAX_MATERIALS)
+        return fail(DRT_CUDA_E_ARG, "%d surfaces / %d materials out of range", scene->num_surfaces, scene->num_materials);
+    if(scene->base_material < 0 || scene->escape_material < 0) return fail(DRT_CUDA_E_UNSUPPORTED, "scene needs a base_material and an escape_material");
+    uint32_t i0 = (uint32_t)((DRT_TRANS_WL - scene->min_wl) / scene->wl_interval);
+    if(DRT_TRANS_WL < scene->min_wl || (int)i0 + 1 >= n) return fail(DRT_CUDA_E_UNSUPPORTED, "630 nm (trans_wl, daily_ray_trace.c:381) lies outside the wavelength grid");
+    for(int i = 0; i < scene->num_surfaces; i += 1)
+        if(scene->surfaces[i].material < 0 || scene->surfaces[i].material >= scene->num_materials) return fail(DRT_CUDA_E_ARG, "surface %d: bad material index", i);
+
+    GeomT<float> *g32 = new GeomT<float>();
+    GeomT<double> *g64 = new GeomT<double>();
+    fill_geom(g32, scene, camera);
+    fill_geom(g64, scene, camera);
+
+    /* spectrum pool: row 0 = zeros, then one row per SPD a material was given */
+    SpdIndex index;
+    memset(&index, 0, sizeof(index));
+    index.n = n; index.nslots = (n + 31) / 32; index.npad = index.nslots * 32;
+    std::vector<float> pool((size_t)index.npad, 0.f);
+    int rows = 1;
+    for(int m = 0; m < scene->num_materials; m += 1)
+        for(int k = 0; k < DRT_SPD_COUNT; k += 1)
+        {
+            if(!(scene->materials[m].spd_mask & (1 << k))) continue;
+            index.row[m][k] = rows++;
+            size_t at = pool.size();
+            pool.resize(at + (size_t)index.npad, 0.f);
+            for(int i = 0; i < n; i += 1) pool[at + (size_t)i] = (float)scene->materials[m].spd[k][i];
+        }
+    index.nrows = rows;
+
+    std::vector<unsigned char> rgbt(drt_rgb_tables_bytes());
+    drt_fill_rgb_tables(rgbt.data(), tables);
+
+    cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool); cudaFree(ctx->d_rgb_tables);
+    ctx->d_geom32 = ctx->d_geom64 = nullptr; ctx->d_index = nullptr; ctx->d_pool = nullptr; ctx->d_rgb_tables = nullptr;
+    ctx->have_scene = false;
+    cudaError_t e = cudaSuccess;
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_geom32, sizeof(GeomT<float>));
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_geom64, sizeof(GeomT<double>));
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_index, sizeof(SpdIndex));
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_pool, pool.size() * 4);
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_rgb_tables, rgbt.size());
+    if(e == cudaSuccess) e = cudaMemcpy(ctx->d_geom32, g32, sizeof(GeomT<float>), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess) e = cudaMemcpy(ctx->d_geom64, g64, sizeof(GeomT<double>), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess) e = cudaMemcpy(ctx->d_index, &index, sizeof(index), cudaMemcpyHostToDevice);
+    if(e == cudaSuccess) e = cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice);
+    if(e == cudaSuccess) e = cudaMemcpy(ctx->d_rgb_tables, rgbt.data(), rgbt.size(), cudaMemcpyHostToDevice);
+    int nlights = g32->nlights;
+    delete g32; delete g64;
+    if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "scene upload: %s", cudaGetErrorString(e));
+    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->pool_words = (uint32_t)pool.size();
+    ctx->have_scene = true;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_set_geometry_precision(drt_cuda_context *ctx, int precision)
+{
+    if(!ctx || (precision != DRT_GEOMETRY_F32 && precision != DRT_GEOMETRY_F64)) return fail(DRT_CUDA_E_ARG, "bad precision");
+    ctx->f64_geometry = precision == DRT_GEOMETRY_F64;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, uint32_t height, size_t *spectral, size_t *filter)
+{
+    if(!ctx || !ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    if(spectral) *spectral = (size_t)width * height * (size_t)ctx->n * 4;
+    if(filter) *filter = (size_t)width * height * 4;
+    return DRT_CUDA_OK;
+}
+
+static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                  FilmPtrs film, float *dump, int accumulate, cudaStream_t stream)
+{
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
+    if(p->sample_end <= p->sample_begin) return fail(DRT_CUDA_E_ARG, "empty sample range [%u,%u)", p->sample_begin, p->sample_end);
+    if(p->max_depth == 0) return fail(DRT_CUDA_E_ARG, "max_depth 0");
+    CU(cudaSetDevice(ctx->device));
+    RenderLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.geom = ctx->f64_geometry ? ctx->d_geom64 : ctx->d_geom32;
+    L.spd_index = ctx->d_index; L.pool = ctx->d_pool; L.pool_words = ctx->pool_words;
+    L.film = film; L.path_dump = dump; L.stats = ctx->d_stats; L.task_counter = ctx->d_counter;
+    L.width = p->width; L.height = p->height; L.x0 = x0; L.y0 = y0; L.x1 = x1; L.y1 = y1;
+    L.sample_begin = p->sample_begin; L.sample_end = p->sample_end; L.max_depth = p->max_depth;
+    L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
+    uint32_t spp = p->sample_end - p->sample_begin;
+    L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
+    L.bounce_words = 3 + 9 * (uint32_t)ctx->nlights + 8;
+    L.path_words = 2 + p->max_depth * L.bounce_words;
+    /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
+    int warps = DRT_CTA_WARPS;
+    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps);
+    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps); }
+    if(smem > ctx->smem_optin)
+        return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
+                    p->max_depth, ctx->nlights, smem, ctx->smem_optin);
+    int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    int by_threads = 16 / warps;    /* 128 registers per thread: at most 16 resident warps per SM */
+    if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if(ctas_per_sm < 1) ctas_per_sm = 1;
+    uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
+    uint64_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+    uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
+    uint64_t need = (ntasks + warps - 1) / warps;
+    if(grid > need) grid = need;
+    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), stream));
+    cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->nslots, (int)grid, warps, smem, stream);
+    if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
+    ctx->launches += 1;
+    ctx->last_launches = 1;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_render_device(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film, int accumulate, void *stream)
+{
+    if(!ctx || !params || !film || !film->sum || !film->filter || !film->mean || !film->m2) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    FilmPtrs f = { film->sum, film->filter, film->mean, film->m2 };
+    return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, accumulate, (cudaStream_t)stream);
+}
+
+static int ensure(float **buf, size_t *have, size_t need)
+{
+    if(*have >= need) return DRT_CUDA_OK;
+    cudaFree(*buf); *buf = nullptr; *have = 0;
+    CU(cudaMalloc(buf, need));
+    *have = need;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *out)
+{
+    if(!ctx || !params || !out || !out->sum || !out->filter || !out->mean || !out->m2) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    CU(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)params->width * params->height, plane = npix * (size_t)ctx->n * 4, fplane = npix * 4;
+    int rc = ensure(&ctx->d_film, &ctx->film_bytes, 3 * plane + fplane);
+    if(rc != DRT_CUDA_OK) return rc;
+    float *base = ctx->d_film;
+    FilmPtrs f = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
+    rc = launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, 0);
+    if(rc != DRT_CUDA_OK) return rc;
+    CU(cudaMemcpyAsync(out->sum, f.sum, plane, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out->mean, f.mean, plane, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out->m2, f.m2, plane, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out->filter, f.filter, fplane, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out)
+{
+    if(!ctx || !out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    DeviceStats s;
+    CU(cudaMemcpy(&s, ctx->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->paths = s.paths; out->closest_rays = s.closest_rays; out->shadow_rays = s.shadow_rays;
+    out->shaded_bounces = s.shaded_bounces; out->rng_draws = s.rng_draws;
+    for(int i = 0; i < 8; i += 1) out->terminated_at_depth[i] = s.terminated_at_depth[i];
+    out->reached_depth_cap = s.reached_depth_cap;
+    out->kernel_launches = ctx->last_launches;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_sample_paths(drt_cuda_context *ctx, const drt_render_params *params,
+                                     uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, float *out_host)
+{
+    if(!ctx || !params || !out_host) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    if(x1 <= x0 || y1 <= y0 || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "empty rectangle or sample range");
+    CU(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)(x1 - x0) * (y1 - y0) * (params->sample_end - params->sample_begin) * (size_t)ctx->n * 4;
+    int rc = ensure(&ctx->d_dump, &ctx->dump_bytes, bytes);
+    if(rc != DRT_CUDA_OK) return rc;
+    FilmPtrs none = { nullptr, nullptr, nullptr, nullptr };
+    rc = launch(ctx, params, x0, y0, x1, y1, none, ctx->d_dump, 0, 0);
+    if(rc != DRT_CUDA_OK) return rc;
+    CU(cudaMemcpy(out_host, ctx->d_dump, bytes, cudaMemcpyDeviceToHost));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film, uint32_t width, uint32_t height, int which,
+                                    float *rgb_device, uint32_t *bgra_device, void *stream)
+{
+    if(!ctx || !film || which < 0 || which > 2) return fail(DRT_CUDA_E_ARG, "bad argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    CU(cudaSetDevice(ctx->device));
+    const float *plane = which == 0 ? film->sum : which == 1 ? film->mean : film->m2;
+    const float *filter = which == 0 ? film->filter : nullptr;
+    if(!plane || (which == 0 && !filter)) return fail(DRT_CUDA_E_ARG, "film plane is NULL");
+    uint32_t npix = width * height;
+    int grid = ctx->num_sms * 8;
+    drt_launch_film_to_rgb(ctx->d_rgb_tables, plane, filter, which == 2, npix, rgb_device, bgra_device, grid, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_merge(drt_cuda_context *ctx, const drt_film *dst, const drt_film *src, uint32_t width, uint32_t height, void *stream)
+{
+    if(!ctx || !dst || !src) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    CU(cudaSetDevice(ctx->device));
+    FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 }, s = { src->sum, src->filter, src->mean, src->m2 };
+    drt_launch_film_merge(d, s, (uint32_t)ctx->n, (size_t)width * height, ctx->num_sms * 8, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_measure_fp32_peak(drt_cuda_context *ctx, int packed, double *tflops)
+{
+    if(!ctx || !tflops) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    float *d_out = nullptr;
+    CU(cudaMalloc(&d_out, 4));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    const int iters = 4096, grid = ctx->num_sms * 8;
+    double best = 0.0;
+    for(int rep = 0; rep < 5; rep += 1)
+    {
+        CU(cudaEventRecord(a, 0));
+        drt_launch_fma_peak(packed, d_out, iters, grid, 0);
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double flops = (double)grid * 256.0 * (double)iters * 16.0 * 2.0;
+        double t = flops / (ms * 1e-3) / 1e12;
+        if(rep > 0 && t > best) best = t;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d_out);
+    *tflops = best;
+    return DRT_CUDA_OK;
+}

@@ -1,0 +1,86 @@
+/*
+ * csrc/drt_device.cuh -- device-side scene layout and launch descriptors.
+ *
+ * The reference's AoS scene with function pointers (daily_ray_trace.h:78-170) becomes three flat blocks that
+ * every CTA stages once into shared memory:
+ *   GeomT<R>   surfaces SoA (precomputed plane frames), per-material scalars and lobe lists, in the arithmetic
+ *              type R of the geometric phase (float by default, double for the branch-flip diagnostic)
+ *   SpdIndex   material -> row of the spectrum pool for each of its six SPDs (row 0 is all zeros)
+ *   pool       nrows x NPAD floats, NPAD = 32 * (wavelength slots per lane)
+ */
+#pragma once
+#include <stdint.h>
+#include "drt_scene.h"
+
+#define DRT_WARP 32
+#define DRT_MAX_SLOTS 4            /* ceil(DRT_MAX_WAVELENGTHS / 32) */
+#define DRT_CTA_WARPS 8
+#define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
+
+/* spectral basis kinds a BSDF evaluation is expressed in (see eval_weights in drt_kernels.cu) */
+enum { BK_CONST = 0, BK_DIFFUSE, BK_GLOSSY, BK_MIRROR, BK_DIEL_R, BK_COND_ON, BK_COND_MN, BK_COUNT };
+#define EVAL_WORDS (BK_COUNT + 1)  /* 7 weights + the micro-normal cosine of BK_COND_MN */
+
+template <typename R>
+struct GeomT
+{
+    int nsurf, nlights, base_mat, escape_mat, nmat, n, pad0, pad1;
+    R   trans_num, trans_den;      /* (630 - w0), (w1 - w0) of value_at_wl, spectrum.c:150-162 */
+    int type[DRT_MAX_SURFACES], mat[DRT_MAX_SURFACES], light_surf[DRT_MAX_SURFACES];
+    R   px[DRT_MAX_SURFACES], py[DRT_MAX_SURFACES], pz[DRT_MAX_SURFACES], rad[DRT_MAX_SURFACES];
+    R   nx[DRT_MAX_SURFACES], ny[DRT_MAX_SURFACES], nz[DRT_MAX_SURFACES];
+    R   unx[DRT_MAX_SURFACES], uny[DRT_MAX_SURFACES], unz[DRT_MAX_SURFACES], ulen[DRT_MAX_SURFACES];
+    R   vnx[DRT_MAX_SURFACES], vny[DRT_MAX_SURFACES], vnz[DRT_MAX_SURFACES], vlen[DRT_MAX_SURFACES];
+    R   ux[DRT_MAX_SURFACES], uy[DRT_MAX_SURFACES], uz[DRT_MAX_SURFACES];
+    R   vx[DRT_MAX_SURFACES], vy[DRT_MAX_SURFACES], vz[DRT_MAX_SURFACES];
+    R   light_pdf[DRT_MAX_SURFACES];
+    /* materials */
+    int mflags[DRT_MAX_MATERIALS];   /* bit0 is_black_body, bit1 is_emissive */
+    int nlobes[DRT_MAX_MATERIALS], dirf[DRT_MAX_MATERIALS];
+    unsigned char lobes[DRT_MAX_MATERIALS][DRT_MAX_LOBES];
+    R   shin[DRT_MAX_MATERIALS], rough[DRT_MAX_MATERIALS];
+    R   n630[DRT_MAX_MATERIALS];                                  /* value_at_wl(refract, 630) */
+    R   refr_a[DRT_MAX_MATERIALS], refr_b[DRT_MAX_MATERIALS];     /* refract samples bracketing 630 nm */
+    /* camera, daily_ray_trace.h:158-170 */
+    R   fwd[3], right[3], up[3], ap_pos[3], film_bl[3];
+    R   ap_radius, focal_depth, pixel_w, pixel_h;
+    R   lens_rot[9];
+};
+
+struct SpdIndex
+{
+    int n, nslots, npad, nrows;
+    int row[DRT_MAX_MATERIALS][DRT_SPD_COUNT];
+};
+
+struct FilmPtrs { float *sum, *filter, *mean, *m2; };
+
+struct DeviceStats
+{
+    unsigned long long paths, closest_rays, shadow_rays, shaded_bounces, rng_draws;
+    unsigned long long terminated_at_depth[8];
+    unsigned long long reached_depth_cap;
+};
+
+struct RenderLaunch
+{
+    const void     *geom;          /* GeomT<float> or GeomT<double> in global memory */
+    const SpdIndex *spd_index;
+    const float    *pool;
+    FilmPtrs        film;
+    float          *path_dump;     /* optional per-path spectra, [pixel_local][sample][N] */
+    DeviceStats    *stats;
+    unsigned int   *task_counter;
+    uint32_t width, height;
+    uint32_t x0, y0, x1, y1;       /* pixel rectangle rendered (whole image for a film render) */
+    uint32_t sample_begin, sample_end;
+    uint32_t max_depth;
+    int32_t  pixel_scheme;
+    uint64_t seed;
+    int32_t  accumulate;
+    int32_t  nlights;
+    uint32_t pixels_per_task;      /* contiguous rectangle pixels claimed per warp task */
+    uint32_t bounce_words;         /* record words per bounce = 3 + 9*nlights + 8 */
+    uint32_t path_words;           /* record words per path   = 2 + max_depth*bounce_words */
+    uint32_t geom_bytes, pool_words;
+};

@@ -1,0 +1,910 @@
+/*
+ * csrc/drt_kernels.cu -- the render hot path as one persistent sm_100a kernel.
+ *
+ * What the reference does per camera path (sample_scene -> cast_ray -> ..., src/daily_ray_trace.c:432-618) is split
+ * along the one axis that never feeds back: NOTHING geometric depends on wavelength (refraction uses n(630 nm) only,
+ * Q10; reflect-or-transmit draws against R(630 nm), bdsf.c:241-247).  So every warp alternates two phases:
+ *
+ *   phase 1 "trace"   one THREAD per path.  Camera ray + per-path Philox stream (K1), closest hit over the SoA scene in
+ *                     shared memory (K2), light sampling + shadow rays (K3), direction sampling (K4).  All spectral
+ *                     quantities are reduced to a handful of scalar WEIGHTS per BSDF evaluation (eval_weights) and
+ *                     written as a compact path record to shared memory.
+ *   phase 2 "shade"   one WARP per path, wavelengths across lanes (3 slots per lane for N = 69).  The record is
+ *                     broadcast, spectra are conflict-free shared-memory rows, throughput / radiance live in registers,
+ *                     and the pixel's film (sum, Welford mean and M2, daily_ray_trace.c:732-743) stays in registers
+ *                     for ALL samples of the pixel: each film plane is written to HBM exactly once, coalesced (K6).
+ *
+ * No path state ever goes to global memory; HBM traffic is the film write, so the kernel is bound by FP32 issue, not
+ * by the 1.2 KB-per-bounce queue traffic of a global-memory wavefront.
+ * Quirk numbers (Qn) refer to SURVEY.md Appendix A; the CPU restatement of the same lines is oracle/drt_oracle.c.
+ */
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "drt_device.cuh"
+#include "drt_rng.h"
+
+namespace drt {
+
+/* ------------------------------------------------------------------ small vector algebra in the phase-1 type R */
+
+template <typename R> struct V3 { R x, y, z; };
+
+template <typename R> __device__ __forceinline__ V3<R> mk(R x, R y, R z) { V3<R> v; v.x = x; v.y = y; v.z = z; return v; }
+template <typename R> __device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return mk<R>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename R> __device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return mk<R>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename R> __device__ __forceinline__ V3<R> operator*(V3<R> a, R f) { return mk<R>(f * a.x, f * a.y, f * a.z); }
+template <typename R> __device__ __forceinline__ V3<R> neg(V3<R> a) { return mk<R>(-a.x, -a.y, -a.z); }
+template <typename R> __device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b)
+{
+    return mk<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+__device__ __forceinline__ float  r_sqrt(float x)  { return sqrtf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float  r_abs(float x)   { return fabsf(x); }
+__device__ __forceinline__ double r_abs(double x)  { return fabs(x); }
+__device__ __forceinline__ float  r_pow(float x, float y)   { return powf(x, y); }
+__device__ __forceinline__ double r_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ void   r_sincos(float t, float *s, float *c)    { sincosf(t, s, c); }
+__device__ __forceinline__ void   r_sincos(double t, double *s, double *c) { sincos(t, s, c); }
+
+template <typename R> struct Num;
+template <> struct Num<float>
+{
+    static __device__ __forceinline__ float pi()  { return 3.14159265358979323846f; }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    static __device__ __forceinline__ float fudge() { return 0.0001f; }
+    /* rng() of rng.c:2-7: r31 / RAND_MAX, rounded once to f32 */
+    static __device__ __forceinline__ float unit(uint32_t r31) { return __uint2float_rn(r31) * 4.6566128752457969e-10f; }
+};
+template <> struct Num<double>
+{
+    static __device__ __forceinline__ double pi()  { return 3.14159265358979323846; }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    static __device__ __forceinline__ double fudge() { return 0.0001; }
+    static __device__ __forceinline__ double unit(uint32_t r31) { return (double)r31 / 2147483647.0; }
+};
+
+template <typename R> __device__ __forceinline__ V3<R> normalise(V3<R> v)
+{
+    R len = r_sqrt(dot(v, v));
+    return mk<R>(v.x / len, v.y / len, v.z / len);
+}
+template <typename R> __device__ __forceinline__ V3<R> reflect(V3<R> v, V3<R> n)   /* geometry.c:85-90 */
+{
+    R f = R(2) * dot(v, n);
+    return v - n * f;
+}
+template <typename R> __device__ __forceinline__ V3<R> transmit(V3<R> v, V3<R> n, R ir, R tr)   /* geometry.c:92-106 */
+{
+    R vn = dot(v, n);
+    R rel = ir / tr;
+    V3<R> m = n * vn;
+    v = m - v;
+    V3<R> perpend = neg(v * rel);
+    R pd = -r_sqrt(R(1) - dot(perpend, perpend));
+    return perpend + n * pd;
+}
+
+/* find_rotation_between_vectors((0,0,1), n) applied to q (geometry.c:263-295), in closed form:
+ * R q = q + a x q + a x (a x q) / (1 + c) with a = (0,0,1) x n, c = n.z; antiparallel -> -q (Q14). */
+template <typename R> __device__ __forceinline__ V3<R> rotate_from_z(V3<R> n, V3<R> q)
+{
+    V3<R> a = mk<R>(-n.y, n.x, R(0));
+    R c = n.z;
+    if(dot(a, a) == R(0) && c <= R(0)) return neg(q);
+    V3<R> aq = cross(a, q);
+    V3<R> aaq = cross(a, aq);
+    R f = R(1) / (R(1) + c);
+    return (q + aq) + aaq * f;
+}
+
+/* ------------------------------------------------------------------ per-path random stream (include/drt_rng.h) */
+
+struct Rng
+{
+    uint32_t key0, key1, seed_lo, seed_hi, draws;
+    uint32_t buf[4];
+    __device__ __forceinline__ void begin(uint64_t seed, uint32_t pixel, uint32_t sample)
+    {
+        key0 = pixel; key1 = sample; seed_lo = (uint32_t)seed; seed_hi = (uint32_t)(seed >> 32); draws = 0;
+    }
+    __device__ __forceinline__ uint32_t next31()
+    {
+        uint32_t lane = draws & 3u;
+        if(lane == 0) drt_philox4x32_10(draws >> 2, 0u, seed_lo, seed_hi, key0, key1, buf);
+        draws += 1;
+        uint32_t w = (lane == 0) ? buf[0] : (lane == 1) ? buf[1] : (lane == 2) ? buf[2] : buf[3];
+        return w >> 1;
+    }
+    template <typename R> __device__ __forceinline__ R unit() { return Num<R>::unit(next31()); }
+};
+
+/* ------------------------------------------------------------------ K2: closest hit / any hit over the SoA scene */
+
+template <typename R> __device__ __forceinline__ R hit_sphere(V3<R> o, V3<R> d, V3<R> c, R r)   /* geometry.c:123-146 */
+{
+    V3<R> co = o - c;
+    R b = R(-2) * dot(co, d);
+    R cc = dot(co, co) - r * r;
+    R disc = b * b - R(4) * cc;
+    if(disc < R(0)) return Num<R>::inf();
+    R sq = r_sqrt(disc);
+    R s0 = (b + sq) / R(2);
+    R s1 = (b - sq) / R(2);
+    if(s0 < R(0) && s1 < R(0)) return Num<R>::inf();
+    if(s0 >= R(0) && s1 < R(0)) return s0;
+    if(s1 >= R(0) && s0 < R(0)) return s1;
+    return (s0 <= s1) ? s0 : s1;
+}
+
+template <typename R> __device__ __forceinline__ R hit_plane(const GeomT<R> &g, int i, V3<R> o, V3<R> d)   /* geometry.c:157-182 */
+{
+    V3<R> n = mk<R>(g.nx[i], g.ny[i], g.nz[i]);
+    V3<R> p = mk<R>(g.px[i], g.py[i], g.pz[i]);
+    R dn = dot(d, n);
+    if(dn == R(0)) return Num<R>::inf();
+    R l = dot(p - o, n) / dn;
+    V3<R> j = (o + d * l) - p;
+    R ju = dot(j, mk<R>(g.unx[i], g.uny[i], g.unz[i]));
+    R jv = dot(j, mk<R>(g.vnx[i], g.vny[i], g.vnz[i]));
+    bool inside = l >= R(0) && R(0) <= ju && ju <= g.ulen[i] && R(0) <= jv && jv <= g.vlen[i];   /* inclusive bounds, Q21 */
+    return inside ? l : Num<R>::inf();
+}
+
+template <typename R> __device__ __forceinline__ R hit_surface(const GeomT<R> &g, int i, V3<R> o, V3<R> d)
+{
+    if(g.type[i] == DRT_GEO_SPHERE) return hit_sphere<R>(o, d, mk<R>(g.px[i], g.py[i], g.pz[i]), g.rad[i]);
+    return hit_plane<R>(g, i, o, d);
+}
+
+template <typename R> struct Hit
+{
+    V3<R> pos, nrm, out;
+    R on_dot;
+    int surf_mat, inc_mat, trans_mat;
+};
+
+/* find_ray_intersection, daily_ray_trace.c:334-403.  Returns false on a miss (escape material). */
+template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R> &g, V3<R> o, V3<R> d, Hit<R> &h)
+{
+    R best = Num<R>::inf();
+    int found = -1;
+    o = o + d * Num<R>::fudge();   /* Q2 */
+    for(int i = 0; i < g.nsurf; i += 1)
+    {
+        int t = g.type[i];
+        if(t != DRT_GEO_SPHERE && t != DRT_GEO_PLANE) continue;
+        R dist = hit_surface<R>(g, i, o, d);
+        if(dist < best) { best = dist; found = i; }   /* strict <: lowest index wins ties */
+    }
+    if(found < 0) return false;
+    h.pos = o + d * best;
+    V3<R> n = mk<R>(g.nx[found], g.ny[found], g.nz[found]);
+    bool is_plane = g.type[found] == DRT_GEO_PLANE;
+    if(!is_plane) n = normalise(h.pos - mk<R>(g.px[found], g.py[found], g.pz[found]));
+    h.out = neg(d);
+    h.on_dot = dot(n, h.out);
+    int sm = g.mat[found];
+    h.surf_mat = sm; h.trans_mat = sm; h.inc_mat = g.base_mat;
+    if(h.on_dot < R(0))
+    {
+        if(!is_plane) { h.trans_mat = g.base_mat; h.inc_mat = sm; }   /* Q11 */
+        n = neg(n);
+        h.on_dot = dot(n, h.out);
+    }
+    h.nrm = n;
+    return true;
+}
+
+/* points_mutually_visible, daily_ray_trace.c:238-270 */
+template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g, V3<R> p0, V3<R> p1)
+{
+    V3<R> dir = normalise(p1 - p0);
+    V3<R> o = p0 + dir * Num<R>::fudge();
+    V3<R> po = p1 - o;
+    R vis_dist = r_sqrt(dot(po, po)) - Num<R>::fudge();
+    for(int i = 0; i < g.nsurf; i += 1)
+    {
+        int t = g.type[i];
+        if(t != DRT_GEO_SPHERE && t != DRT_GEO_PLANE) continue;
+        if(hit_surface<R>(g, i, o, dir) < vis_dist) return false;
+    }
+    return true;
+}
+
+/* ------------------------------------------------------------------ BSDF evaluation reduced to basis weights
+ *
+ * bdsf() (daily_ray_trace.c:215-229) sums the material's lobes through ONE scratch spectrum that is zeroed once;
+ * lobes that "do not write" leave the previous lobe's value in it (Q7).  Every lobe output is a scalar times one of
+ * seven spectra: 1, diffuse, glossy, mirror, R_dielectric(on_dot), F_conductor(on_dot), F_conductor(mn_dot).  Walking
+ * the lobe list with a 7-vector as the scratch reproduces the sum, stale values included, as 7 weights. */
+template <typename R>
+__device__ __forceinline__ void eval_weights(const GeomT<R> &g, const Hit<R> &h, V3<R> in, bool is_reflection, bool is_transmission,
+                                             float scale, float w[EVAL_WORDS])
+{
+    float cur[BK_COUNT], acc[BK_COUNT];
+#pragma unroll
+    for(int k = 0; k < BK_COUNT; k += 1) { cur[k] = 0.f; acc[k] = 0.f; }
+    float mn_cos = 0.f;
+    int m = h.surf_mat;
+    int nl = g.nlobes[m];
+    for(int li = 0; li < nl; li += 1)
+    {
+        int lobe = g.lobes[m][li];
+        bool wrote = true;
+        int kind = BK_CONST;
+        float val = 0.f, val_const = 0.f;
+        switch(lobe)
+        {
+            case DRT_LOBE_BP_DIFFUSE:   /* bdsf.c:105-109 */
+                kind = BK_DIFFUSE; val = (float)((R(1) / Num<R>::pi()) * r_abs(dot(h.nrm, in)));
+                break;
+            case DRT_LOBE_BP_GLOSSY:   /* bdsf.c:111-119 */
+            {
+                V3<R> bis = normalise(h.out + in);
+                R nb = dot(h.nrm, bis);
+                R coef = r_pow((R(0) > nb) ? R(0) : nb, g.shin[m]);
+                kind = BK_GLOSSY; val = (float)(coef * r_abs(dot(h.nrm, in)));
+                break;
+            }
+            case DRT_LOBE_MIRROR:   /* bdsf.c:121-132: zero on mismatch */
+                kind = BK_MIRROR; val = is_reflection ? 1.f : 0.f;
+                break;
+            case DRT_LOBE_FS_CONDUCTOR:   /* bdsf.c:134-146: no write on mismatch (Q8: exact match == "came from the reflect formula") */
+                kind = BK_COND_ON; val = 1.f; wrote = is_reflection;
+                break;
+            case DRT_LOBE_FS_DIELECTRIC_REFLECTANCE:   /* bdsf.c:148-159 */
+                kind = BK_DIEL_R; val = 1.f; wrote = is_reflection;
+                break;
+            case DRT_LOBE_FS_DIELECTRIC_TRANSMITTANCE:   /* bdsf.c:161-172: 1 - R */
+                kind = BK_DIEL_R; val = -1.f; val_const = 1.f; wrote = is_transmission;
+                break;
+            case DRT_LOBE_CT_CONDUCTOR:   /* bdsf.c:174-186 */
+            {
+                V3<R> mn = normalise(h.out + in);
+                R mn_dot = r_abs(dot(h.nrm, mn));
+                /* ggx_att(out, n, mn, rough) * 1/(4 on_dot), bdsf.c:3-42 */
+                R rough = g.rough[m], r2 = rough * rough;
+                R d = dot(h.nrm, mn), gg = R(0);
+                if(d > R(0))
+                {
+                    R d2 = d * d, d4 = d2 * d2, tan_sq = (R(1) / d2) - R(1);
+                    gg = r2 / (Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
+                }
+                R v_mn = dot(h.out, mn), v_sn = dot(h.out, h.nrm);
+                R quot = r_abs(v_mn / v_sn), att = R(0);
+                if(!(quot <= R(0)))
+                {
+                    R tan_sq = (R(1) / (v_sn * v_sn)) - R(1);
+                    att = R(2) / (R(1) + r_sqrt(R(1) + r2 * tan_sq));
+                }
+                kind = BK_COND_MN; val = (float)((gg * att) * (R(1) / (R(4) * h.on_dot)));
+                mn_cos = (float)mn_dot;
+                break;
+            }
+            default: wrote = false; break;
+        }
+        if(wrote)
+        {
+#pragma unroll
+            for(int k = 0; k < BK_COUNT; k += 1) cur[k] = 0.f;
+#pragma unroll
+            for(int k = 0; k < BK_COUNT; k += 1) if(k == kind) cur[k] = val;
+            cur[BK_CONST] += val_const;
+        }
+#pragma unroll
+        for(int k = 0; k < BK_COUNT; k += 1) acc[k] += cur[k];
+    }
+#pragma unroll
+    for(int k = 0; k < BK_COUNT; k += 1) w[k] = acc[k] * scale;
+    w[BK_COUNT] = mn_cos;
+}
+
+/* dielectric Fresnel at one wavelength, bdsf.c:44-66 (Q9 kept) */
+template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr, T inc_cos)
+{
+    T inc_sin_sq = T(1) - inc_cos * inc_cos;
+    T rel = ir / tr;
+    T ts_sin_sq = rel * rel * inc_sin_sq;
+    if(ts_sin_sq >= T(1)) return T(1);
+    T ts_cos = sqrt(T(1) - ts_sin_sq * ts_sin_sq);
+    T tr_on = tr * inc_cos, tr_ts = tr * ts_cos, ir_on = ir * inc_cos, ir_ts = ir * ts_cos;
+    T par = (tr_on - ir_ts) / (tr_on + ir_ts);
+    T per = (ir_on - tr_ts) / (ir_on + tr_ts);
+    return T(0.5) * (par * par + per * per);
+}
+
+/* conductor Fresnel at one wavelength, bdsf.c:78-101 */
+__device__ __forceinline__ float fresnel_conductor(float ir, float tr, float te, float inc_cos)
+{
+    float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
+    float eta = tr / ir, kap = te / ir;
+    float eta_sq = eta * eta, kap_sq = kap * kap;
+    float r = eta_sq - kap_sq - sin_sq;
+    float apb_sq = sqrtf(r * r + 4.f * eta_sq * kap_sq);
+    float a = sqrtf(0.5f * (apb_sq + r));
+    float s = apb_sq + cos_sq;
+    float t = 2.f * a * inc_cos;
+    float u = cos_sq * apb_sq + sin_sq * sin_sq;
+    float v = t * sin_sq;
+    float par = (s - t) / (s + t);
+    float per = par * (u - v) / (u + v);
+    return 0.5f * (par + per);
+}
+
+/* ------------------------------------------------------------------ K4: the six direction samplers, bdsf.c:191-292 */
+
+template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /* uniform_sample_disc, rng.c:25-51 */
+{
+    R rx = rng.unit<R>();
+    R ry = rng.unit<R>();
+    R ox = R(2) * rx - R(1), oy = R(2) * ry - R(1);
+    if(ox == R(0) && oy == R(0)) return mk<R>(R(0), R(0), R(0));
+    R r, t;
+    if(r_abs(ox) > r_abs(oy)) { r = ox; t = (Num<R>::pi() / R(4)) * (oy / ox); }
+    else                      { r = oy; t = (Num<R>::pi() / R(2)) - (Num<R>::pi() / R(4)) * (ox / oy); }
+    R s, c;
+    r_sincos(t, &s, &c);
+    return mk<R>(r * c, r * s, R(0));
+}
+
+template <typename R>
+__device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R> &h, Rng &rng, V3<R> &in, R &inv_pdf,
+                                                 bool &is_reflection, bool &is_transmission)
+{
+    int m = h.surf_mat;
+    is_reflection = false; is_transmission = false;
+    in = mk<R>(R(0), R(0), R(0)); inv_pdf = R(0);
+    switch(g.dirf[m])
+    {
+        case DRT_DIR_UNIFORM_HEMISPHERE:   /* :191-198; uniform_sample_sphere rng.c:14-23 has z = u >= 0 */
+        {
+            R u = rng.unit<R>();
+            R v = rng.unit<R>();
+            R r = r_sqrt(R(1) - u * u);
+            R s, c;
+            r_sincos(R(2) * Num<R>::pi() * v, &s, &c);
+            in = rotate_from_z<R>(h.nrm, mk<R>(r * c, r * s, u));
+            inv_pdf = R(2) * Num<R>::pi();
+            break;
+        }
+        case DRT_DIR_COS_WEIGHTED_HEMISPHERE:   /* :200-213 */
+        {
+            V3<R> q;
+            for(;;)
+            {
+                q = sample_disc<R>(rng);
+                if(dot(q, q) < R(1)) break;   /* Q16 */
+            }
+            q.z = r_sqrt(R(1) - dot(q, q));
+            in = rotate_from_z<R>(h.nrm, q);
+            inv_pdf = Num<R>::pi() / dot(h.nrm, in);
+            break;
+        }
+        case DRT_DIR_SPECULAR:   /* :215-220 */
+            in = reflect<R>(neg(h.out), h.nrm);
+            inv_pdf = R(1);
+            is_reflection = true;
+            break;
+        case DRT_DIR_TRANSMIT:   /* :222-234 */
+            in = transmit<R>(neg(h.out), h.nrm, g.n630[h.inc_mat], g.n630[h.trans_mat]);
+            inv_pdf = R(1);
+            is_transmission = (in.x == in.x) && (in.y == in.y) && (in.z == in.z);
+            break;
+        case DRT_DIR_REFLECT_OR_TRANSMIT:   /* :236-259: reflect with probability R(630 nm) */
+        {
+            R ra = fresnel_dielectric<R>(g.refr_a[h.inc_mat], g.refr_a[h.trans_mat], h.on_dot);
+            R rb = fresnel_dielectric<R>(g.refr_b[h.inc_mat], g.refr_b[h.trans_mat], h.on_dot);
+            R rd = ra + (g.trans_num * ((rb - ra) / g.trans_den));
+            R f = rng.unit<R>();
+            if(f < rd)
+            {
+                in = reflect<R>(neg(h.out), h.nrm);
+                inv_pdf = R(1) / rd;
+                is_reflection = true;
+            }
+            else
+            {
+                in = transmit<R>(neg(h.out), h.nrm, g.n630[h.inc_mat], g.n630[h.trans_mat]);
+                inv_pdf = R(1) / (R(1) - rd);
+                is_transmission = (in.x == in.x) && (in.y == in.y) && (in.z == in.z);
+            }
+            break;
+        }
+        case DRT_DIR_CT:   /* :261-292 */
+        {
+            R rough = g.rough[m];
+            do
+            {
+                R f = rng.unit<R>();
+                R gq = rng.unit<R>();
+                R tan_mn = (rough * r_sqrt(f)) / r_sqrt(R(1) - f);
+                R cos_mn = R(1) / r_sqrt(R(1) + tan_mn * tan_mn);
+                R sin_mn = r_sqrt(R(1) - cos_mn * cos_mn);
+                R s, c;
+                r_sincos(R(2) * Num<R>::pi() * gq, &s, &c);
+                V3<R> mn = rotate_from_z<R>(h.nrm, mk<R>(sin_mn * c, sin_mn * s, cos_mn));
+                R sn_mn = dot(h.nrm, mn);
+                if(sn_mn < R(0)) { mn = neg(mn); sn_mn = -sn_mn; }
+                R o_mn = dot(h.out, mn);
+                in = reflect<R>(neg(h.out), mn);
+                R d = R(0);   /* ggx(n, mn, rough) * sn_mn */
+                if(sn_mn > R(0))
+                {
+                    R r2 = rough * rough, d2 = sn_mn * sn_mn, d4 = d2 * d2, tan_sq = (R(1) / d2) - R(1);
+                    d = r2 / (Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
+                }
+                d = d * sn_mn;
+                inv_pdf = (R(4) * o_mn) / d;
+            }
+            while(dot(in, h.nrm) < R(0));
+            break;
+        }
+        default: break;
+    }
+}
+
+/* ------------------------------------------------------------------ path records in shared memory (SoA per warp) */
+
+#define REC_NB   0
+#define REC_VIG  1
+#define REC_HEAD 2
+#define KIND_SHADE 1u
+#define KIND_EMIT  2u
+
+__device__ __forceinline__ float &rec_at(float *rec, uint32_t field, uint32_t slot) { return rec[field * DRT_WARP + slot]; }
+
+/* ------------------------------------------------------------------ phase 1: trace one path, emit its record */
+
+template <typename R>
+__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLaunch &L, float *rec, uint32_t slot,
+                                               uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
+{
+    Rng rng;
+    rng.begin(L.seed, y * L.width + x, sample);
+
+    /* K1: sample_pixel_point + sample_scene, daily_ray_trace.c:550-607 */
+    R px = R(0), py = R(0);
+    if(L.pixel_scheme == DRT_PIXEL_CENTER) { px = R(0.5); py = R(0.5); }
+    else if(L.pixel_scheme == DRT_PIXEL_RANDOM) { px = rng.unit<R>(); py = rng.unit<R>(); }
+    R film_x = (R(x) + px) * g.pixel_w;
+    R film_y = (R(y) + py) * g.pixel_h;
+    V3<R> fwd = mk<R>(g.fwd[0], g.fwd[1], g.fwd[2]);
+    V3<R> ap = mk<R>(g.ap_pos[0], g.ap_pos[1], g.ap_pos[2]);
+    V3<R> point = (mk<R>(g.right[0], g.right[1], g.right[2]) * film_x + mk<R>(g.up[0], g.up[1], g.up[2]) * film_y)
+                  + mk<R>(g.film_bl[0], g.film_bl[1], g.film_bl[2]);
+    V3<R> o, d;
+    if(g.ap_radius > R(0))
+    {
+        V3<R> focus_dir = normalise(ap - point);
+        focus_dir = focus_dir * (g.focal_depth / dot(focus_dir, fwd));
+        V3<R> focus_point = point + focus_dir;
+        V3<R> disc = sample_disc<R>(rng) * g.ap_radius;
+        V3<R> lens = mk<R>(g.lens_rot[0] * disc.x + g.lens_rot[3] * disc.y + g.lens_rot[6] * disc.z,
+                           g.lens_rot[1] * disc.x + g.lens_rot[4] * disc.y + g.lens_rot[7] * disc.z,
+                           g.lens_rot[2] * disc.x + g.lens_rot[5] * disc.y + g.lens_rot[8] * disc.z);
+        o = ap + lens;
+        d = normalise(focus_point - o);
+    }
+    else
+    {
+        o = point;
+        d = normalise(ap - o);   /* Q1 */
+    }
+    rec_at(rec, REC_VIG, slot) = (float)dot(d, fwd);   /* Q20 */
+
+    uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth;
+    const uint32_t bw = L.bounce_words;
+    for(uint32_t depth = 0; depth < L.max_depth; depth += 1)
+    {
+        Hit<R> h;
+        closest += 1;
+        bool found = closest_hit<R>(g, o, d, h);
+        int m = found ? h.surf_mat : g.escape_mat;
+        int flags = g.mflags[m];
+        uint32_t base = REC_HEAD + nb * bw;
+        if(flags & 1)   /* black body: escape or emitter, cast_ray :451-457 */
+        {
+            if(flags & 2)
+            {
+                rec_at(rec, base, slot) = __uint_as_float(KIND_EMIT | ((uint32_t)m << 2));   /* Q6 */
+                nb += 1;
+            }
+            end_depth = depth;
+            break;
+        }
+        shaded += 1;
+        /* K3: direct_light_contribution, :272-332 -- every emissive surface in index order; draws come before visibility */
+        uint32_t vis_mask = 0;
+        for(int j = 0; j < g.nlights; j += 1)
+        {
+            int ls = g.light_surf[j];
+            int lt = g.type[ls];
+            V3<R> lp = mk<R>(g.px[ls], g.py[ls], g.pz[ls]);
+            R k;
+            if(lt == DRT_GEO_POINT)
+            {
+                V3<R> to = lp - h.pos;
+                R dist = r_sqrt(dot(to, to));
+                k = (R(4) * Num<R>::pi() * dist * dist) * g.light_pdf[ls];   /* Q3 */
+            }
+            else if(lt == DRT_GEO_SPHERE)
+            {
+                R u = rng.unit<R>();
+                R v = rng.unit<R>();
+                R r = r_sqrt(R(1) - u * u);
+                R s, c;
+                r_sincos(R(2) * Num<R>::pi() * v, &s, &c);
+                lp = lp + mk<R>(r * c, r * s, u) * g.rad[ls];   /* Q5 */
+                k = g.light_pdf[ls];
+            }
+            else
+            {
+                R u = rng.unit<R>();
+                R v = rng.unit<R>();
+                lp = (lp + mk<R>(g.ux[ls], g.uy[ls], g.uz[ls]) * u) + mk<R>(g.vx[ls], g.vy[ls], g.vz[ls]) * v;
+                k = g.light_pdf[ls];
+            }
+            shadow += 1;
+            if(visible<R>(g, h.pos, lp))
+            {
+                float w[EVAL_WORDS];
+                eval_weights<R>(g, h, normalise(lp - h.pos), false, false, 1.f, w);
+                uint32_t e = base + 3 + 9 * (uint32_t)j;
+#pragma unroll
+                for(int q = 0; q < EVAL_WORDS; q += 1) rec_at(rec, e + q, slot) = w[q];
+                rec_at(rec, e + 8, slot) = (float)k;
+                vis_mask |= 1u << j;
+            }
+        }
+        /* K4: sample the next direction and evaluate the BSDF for it, cast_ray :464-472 */
+        V3<R> in; R inv_pdf; bool is_refl, is_trans;
+        sample_direction<R>(g, h, rng, in, inv_pdf, is_refl, is_trans);
+        {
+            float w[EVAL_WORDS];
+            eval_weights<R>(g, h, in, is_refl, is_trans, (float)inv_pdf, w);
+            uint32_t e = base + 3 + 9 * (uint32_t)g.nlights;
+#pragma unroll
+            for(int q = 0; q < EVAL_WORDS; q += 1) rec_at(rec, e + q, slot) = w[q];
+        }
+        rec_at(rec, base + 0, slot) = __uint_as_float(KIND_SHADE | ((uint32_t)h.surf_mat << 2) | ((uint32_t)h.inc_mat << 7) | ((uint32_t)h.trans_mat << 12));
+        rec_at(rec, base + 1, slot) = __uint_as_float(vis_mask);
+        rec_at(rec, base + 2, slot) = (float)h.on_dot;
+        nb += 1;
+        d = in;
+        o = h.pos;
+    }
+    rec_at(rec, REC_NB, slot) = __uint_as_float(nb);
+
+    tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
+    return (end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8;   /* histogram bin: depth of termination, 8 = hit the cap */
+}
+
+/* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp */
+
+template <int NS>
+__device__ __forceinline__ void eval_spectrum(const float *rec, uint32_t e, uint32_t slot, const SpdIndex &ix, const float *pool,
+                                              int surf_mat, int inc_mat, int trans_mat, float on_dot, uint32_t lane,
+                                              bool &have_r, float (&rl)[NS], bool &have_f, float (&fl)[NS], float (&f)[NS])
+{
+    float w[EVAL_WORDS];
+#pragma unroll
+    for(int q = 0; q < EVAL_WORDS; q += 1) w[q] = rec[(e + q) * DRT_WARP + slot];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) f[k] = w[BK_CONST];
+    if(w[BK_DIFFUSE] != 0.f)
+    {
+        const float *row = pool + ix.row[surf_mat][DRT_SPD_DIFFUSE] * ix.npad + lane;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_DIFFUSE], row[k * DRT_WARP], f[k]);
+    }
+    if(w[BK_GLOSSY] != 0.f)
+    {
+        const float *row = pool + ix.row[surf_mat][DRT_SPD_GLOSSY] * ix.npad + lane;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_GLOSSY], row[k * DRT_WARP], f[k]);
+    }
+    if(w[BK_MIRROR] != 0.f)
+    {
+        const float *row = pool + ix.row[surf_mat][DRT_SPD_MIRROR] * ix.npad + lane;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_MIRROR], row[k * DRT_WARP], f[k]);
+    }
+    if(w[BK_DIEL_R] != 0.f)
+    {
+        if(!have_r)
+        {
+            const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+            const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) rl[k] = fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot);
+            have_r = true;
+        }
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_DIEL_R], rl[k], f[k]);
+    }
+    if(w[BK_COND_ON] != 0.f)
+    {
+        if(!have_f)
+        {
+            const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+            const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+            const float *te = pool + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad + lane;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) fl[k] = fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot);
+            have_f = true;
+        }
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_COND_ON], fl[k], f[k]);
+    }
+    if(w[BK_COND_MN] != 0.f)
+    {
+        const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+        const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+        const float *te = pool + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad + lane;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+            f[k] = fmaf(w[BK_COND_MN], fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], w[BK_COUNT]), f[k]);
+    }
+}
+
+/* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from the record; returns the path contribution
+ * already multiplied by the vignette factor (:612-615). */
+template <int NS, typename G>
+__device__ __forceinline__ void replay_path(const float *rec, uint32_t slot, const G &g, const SpdIndex &ix, const float *pool,
+                                            const RenderLaunch &L, uint32_t lane, float (&c)[NS])
+{
+    float thr[NS], dst[NS];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) { thr[k] = 1.f; dst[k] = 0.f; }
+    uint32_t nb = __float_as_uint(rec[REC_NB * DRT_WARP + slot]);
+    const uint32_t bw = L.bounce_words;
+    for(uint32_t b = 0; b < nb; b += 1)
+    {
+        uint32_t base = REC_HEAD + b * bw;
+        uint32_t hdr = __float_as_uint(rec[base * DRT_WARP + slot]);
+        int surf_mat = (hdr >> 2) & 31;
+        if((hdr & 3u) == KIND_EMIT)
+        {
+            const float *row = pool + ix.row[surf_mat][DRT_SPD_EMISSION] * ix.npad + lane;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], row[k * DRT_WARP], dst[k]);
+            break;
+        }
+        int inc_mat = (hdr >> 7) & 31, trans_mat = (hdr >> 12) & 31;
+        uint32_t vis = __float_as_uint(rec[(base + 1) * DRT_WARP + slot]);
+        float on_dot = rec[(base + 2) * DRT_WARP + slot];
+        bool have_r = false, have_f = false;
+        float rl[NS], fl[NS], f[NS], contrib[NS];
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) { contrib[k] = 0.f; rl[k] = 0.f; fl[k] = 0.f; }
+        for(int j = 0; j < L.nlights; j += 1)
+        {
+            if(!((vis >> j) & 1u)) continue;
+            uint32_t e = base + 3 + 9 * (uint32_t)j;
+            eval_spectrum<NS>(rec, e, slot, ix, pool, surf_mat, inc_mat, trans_mat, on_dot, lane, have_r, rl, have_f, fl, f);
+            float kk = rec[(e + 8) * DRT_WARP + slot];
+            const float *erow = pool + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION] * ix.npad + lane;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
+        }
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], contrib[k], dst[k]);
+        eval_spectrum<NS>(rec, base + 3 + 9 * (uint32_t)L.nlights, slot, ix, pool, surf_mat, inc_mat, trans_mat, on_dot, lane,
+                          have_r, rl, have_f, fl, f);
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) thr[k] *= f[k];
+    }
+    float vig = rec[REC_VIG * DRT_WARP + slot];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) c[k] = dst[k] * vig;
+}
+
+/* ------------------------------------------------------------------ the kernel */
+
+template <typename R, int NS>
+__global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const RenderLaunch L)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
+    size_t off = (sizeof(GeomT<R>) + 15) & ~size_t(15);
+    SpdIndex *six = reinterpret_cast<SpdIndex *>(smem_raw + off);
+    off += (sizeof(SpdIndex) + 15) & ~size_t(15);
+    float *spool = reinterpret_cast<float *>(smem_raw + off);
+    off += (size_t)L.pool_words * 4;
+    unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem_raw + off);
+    off += 16 * 8;
+    float *srec = reinterpret_cast<float *>(smem_raw + off);
+
+    /* stage the scene once per (persistent) CTA */
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(L.geom);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
+        for(uint32_t i = threadIdx.x; i < sizeof(GeomT<R>) / 4; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint32_t *>(L.spd_index);
+        dst = reinterpret_cast<uint32_t *>(six);
+        for(uint32_t i = threadIdx.x; i < sizeof(SpdIndex) / 4; i += blockDim.x) dst[i] = src[i];
+        for(uint32_t i = threadIdx.x; i < L.pool_words; i += blockDim.x) spool[i] = L.pool[i];
+        if(threadIdx.x < 16) s_stats[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
+    const GeomT<R> &g = *sg;
+    const SpdIndex &ix = *six;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    float *rec = srec + (size_t)warp * L.path_words * DRT_WARP;
+    const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
+    const uint32_t spp = L.sample_end - L.sample_begin;
+    const uint32_t n = (uint32_t)ix.n;
+    const uint32_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+
+    uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
+    uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
+    for(;;)
+    {
+        uint32_t task = 0;
+        if(lane == 0) task = atomicAdd(L.task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if(task >= ntasks) break;
+        uint32_t p_begin = task * L.pixels_per_task;
+        uint32_t p_end = min(p_begin + L.pixels_per_task, npix);
+        uint32_t total = (p_end - p_begin) * spp;
+        traced += total;
+
+        /* film of the pixel being accumulated, in registers: lane holds wavelengths lane, lane+32, ... */
+        float f_sum[NS], f_mean[NS], f_m2[NS], f_cnt = 0.f;
+        uint32_t cur_pixel = 0xffffffffu, cur_gpix = 0;
+
+        for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
+        {
+            uint32_t q = q0 + lane;
+            uint32_t bin = 9;
+            if(q < total)
+            {
+                uint32_t lp = p_begin + q / spp, s = L.sample_begin + q % spp;
+                bin = trace_path<R>(g, L, rec, lane, L.x0 + lp % rw, L.y0 + lp / rw, s, tally);
+            }
+            __syncwarp();
+#pragma unroll
+            for(uint32_t d = 0; d < 9; d += 1)
+            {
+                uint32_t votes = __popc(__ballot_sync(0xffffffffu, bin == d));
+                if(lane == d) hist += votes;
+            }
+            uint32_t count = min((uint32_t)DRT_WARP, total - q0);
+            for(uint32_t slot = 0; slot < count; slot += 1)
+            {
+                uint32_t qq = q0 + slot;
+                uint32_t lp = p_begin + qq / spp;
+                if(lp != cur_pixel)
+                {
+                    if(cur_pixel != 0xffffffffu && L.film.sum)
+                    {
+#pragma unroll
+                        for(int k = 0; k < NS; k += 1)
+                        {
+                            uint32_t wl = lane + k * DRT_WARP;
+                            if(wl < n)
+                            {
+                                size_t at = (size_t)cur_gpix * n + wl;
+                                L.film.sum[at] = f_sum[k]; L.film.mean[at] = f_mean[k]; L.film.m2[at] = f_m2[k];
+                            }
+                        }
+                        if(lane == 0) L.film.filter[cur_gpix] = f_cnt;
+                    }
+                    cur_pixel = lp;
+                    cur_gpix = (L.y0 + lp / rw) * L.width + (L.x0 + lp % rw);
+                    f_cnt = 0.f;
+#pragma unroll
+                    for(int k = 0; k < NS; k += 1) { f_sum[k] = 0.f; f_mean[k] = 0.f; f_m2[k] = 0.f; }
+                    if(L.accumulate && L.film.sum)
+                    {
+                        f_cnt = L.film.filter[cur_gpix];
+#pragma unroll
+                        for(int k = 0; k < NS; k += 1)
+                        {
+                            uint32_t wl = lane + k * DRT_WARP;
+                            if(wl < n)
+                            {
+                                size_t at = (size_t)cur_gpix * n + wl;
+                                f_sum[k] = L.film.sum[at]; f_mean[k] = L.film.mean[at]; f_m2[k] = L.film.m2[at];
+                            }
+                        }
+                    }
+                }
+                float c[NS];
+                replay_path<NS>(rec, slot, g, ix, spool, L, lane, c);
+                /* K6: film accumulation + Welford, daily_ray_trace.c:732-743 (filter weight is the constant 1, Q20) */
+                f_cnt += 1.f;
+                float inv = 1.f / f_cnt;
+#pragma unroll
+                for(int k = 0; k < NS; k += 1)
+                {
+                    f_sum[k] += c[k];
+                    float delta = c[k] - f_mean[k];
+                    f_mean[k] = fmaf(delta, inv, f_mean[k]);
+                    f_m2[k] = fmaf(delta, c[k] - f_mean[k], f_m2[k]);
+                }
+                if(L.path_dump)
+                {
+#pragma unroll
+                    for(int k = 0; k < NS; k += 1)
+                    {
+                        uint32_t wl = lane + k * DRT_WARP;
+                        if(wl < n) L.path_dump[((size_t)lp * spp + qq % spp) * n + wl] = c[k];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if(cur_pixel != 0xffffffffu && L.film.sum)
+        {
+#pragma unroll
+            for(int k = 0; k < NS; k += 1)
+            {
+                uint32_t wl = lane + k * DRT_WARP;
+                if(wl < n)
+                {
+                    size_t at = (size_t)cur_gpix * n + wl;
+                    L.film.sum[at] = f_sum[k]; L.film.mean[at] = f_mean[k]; L.film.m2[at] = f_m2[k];
+                }
+            }
+            if(lane == 0) L.film.filter[cur_gpix] = f_cnt;
+        }
+    }
+
+    /* work counters: one shared-memory atomic per warp per counter, then one global atomic per CTA per counter */
+#pragma unroll
+    for(int k = 0; k < 4; k += 1)
+    {
+        unsigned long long v = tally[k];
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if(lane == 0) atomicAdd(&s_stats[1 + k], v);
+    }
+    if(lane == 0) atomicAdd(&s_stats[0], (unsigned long long)traced);
+    if(lane < 9) atomicAdd(&s_stats[5 + lane], (unsigned long long)hist);
+    __syncthreads();
+    if(threadIdx.x < 14 && s_stats[threadIdx.x])
+        atomicAdd(reinterpret_cast<unsigned long long *>(L.stats) + threadIdx.x, s_stats[threadIdx.x]);
+}
+
+} // namespace drt
+
+/* ------------------------------------------------------------------ launch helper used by drt_capi.cu */
+
+template <typename R>
+static cudaError_t launch_render_ns(const RenderLaunch &L, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
+{
+#define DRT_LAUNCH(NS) do { \
+        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if(e != cudaSuccess) return e; \
+        drt::render_kernel<R, NS><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
+    switch(nslots)
+    {
+        case 1: DRT_LAUNCH(1); break;
+        case 2: DRT_LAUNCH(2); break;
+        case 3: DRT_LAUNCH(3); break;
+        default: DRT_LAUNCH(4); break;
+    }
+#undef DRT_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
+{
+    return f64_geometry ? launch_render_ns<double>(L, nslots, grid, warps, smem, stream) : launch_render_ns<float>(L, nslots, grid, warps, smem, stream);
+}
+
+size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps)
+{
+    size_t geom = f64_geometry ? sizeof(GeomT<double>) : sizeof(GeomT<float>);
+    size_t off = (geom + 15) & ~size_t(15);
+    off += (sizeof(SpdIndex) + 15) & ~size_t(15);
+    off += (size_t)L.pool_words * 4;
+    off += 16 * 8;
+    off += (size_t)warps * L.path_words * DRT_WARP * 4;
+    return off;
+}

@@ -1,0 +1,150 @@
+"""ctypes binding of libdrt_cuda.so: the C ABI of include/drt_cuda.h.
+
+There is no CPU fallback anywhere in this module: if the library is not built, or no CUDA device is visible,
+every entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import PACKAGE_DIR
+from ._structs import Camera, RenderParams, Scene, Tables
+
+GEOMETRY_F32, GEOMETRY_F64 = 0, 1
+
+EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
+           "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
+           "drt_cuda_get_stats", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
+           "drt_cuda_measure_fp32_peak"]
+
+
+class Film(C.Structure):
+    _fields_ = [("sum", C.c_void_p), ("filter", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("shaded_bounces", C.c_uint64), ("rng_draws", C.c_uint64), ("terminated_at_depth", C.c_uint64 * 8),
+                ("reached_depth_cap", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+class CudaError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"drt_cuda error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(PACKAGE_DIR, "libdrt_cuda.so")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: the CUDA extension must be built (make -C {PACKAGE_DIR}); "
+                              "this package has no CPU render path")
+        L = C.CDLL(path)
+        L.drt_cuda_last_error.restype = C.c_char_p
+        L.drt_cuda_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.drt_cuda_destroy.argtypes = [C.c_void_p]
+        L.drt_cuda_destroy.restype = None
+        L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
+        L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
+        L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
+        L.drt_cuda_render_host.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film)]
+        L.drt_cuda_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.drt_cuda_sample_paths.argtypes = [C.c_void_p, C.POINTER(RenderParams)] + [C.c_uint32] * 4 + [C.c_void_p]
+        L.drt_cuda_film_to_rgb.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.drt_cuda_film_merge.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_void_p]
+        L.drt_cuda_measure_fp32_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise CudaError(rc, lib().drt_cuda_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return lib().drt_cuda_device_count()
+
+
+class Context:
+    """One CUDA device with one uploaded scene (drt_cuda_context)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().drt_cuda_create(device, C.byref(self._h)))
+        self.device = device
+        self.n = None
+
+    def close(self):
+        if self._h:
+            lib().drt_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, scene, camera, tables):
+        _check(lib().drt_cuda_upload_scene(self._h, C.byref(scene), C.byref(camera), C.byref(tables)))
+        self.n = scene.num_wavelengths
+
+    def set_geometry_precision(self, precision):
+        _check(lib().drt_cuda_set_geometry_precision(self._h, precision))
+
+    def render_host(self, params):
+        """End-to-end call with host buffers: returns dict of numpy f32 arrays sum[H*W,N], filter[H*W], mean, m2."""
+        npix = params.width * params.height
+        out = {"sum": np.empty((npix, self.n), np.float32), "filter": np.empty(npix, np.float32),
+               "mean": np.empty((npix, self.n), np.float32), "m2": np.empty((npix, self.n), np.float32)}
+        film = Film(out["sum"].ctypes.data, out["filter"].ctypes.data, out["mean"].ctypes.data, out["m2"].ctypes.data)
+        _check(lib().drt_cuda_render_host(self._h, C.byref(params), C.byref(film)))
+        return out
+
+    def render_host_into(self, params, film):
+        _check(lib().drt_cuda_render_host(self._h, C.byref(params), C.byref(film)))
+
+    def render_device(self, params, film, accumulate=False, stream=None):
+        _check(lib().drt_cuda_render_device(self._h, C.byref(params), C.byref(film), int(accumulate), stream))
+
+    def sample_paths(self, params, x0, y0, x1, y1):
+        """The sample_scene seam: f32 array [(y1-y0)*(x1-x0), spp, N] of per-path spectral radiance."""
+        spp = params.sample_end - params.sample_begin
+        out = np.empty(((y1 - y0) * (x1 - x0), spp, self.n), np.float32)
+        _check(lib().drt_cuda_sample_paths(self._h, C.byref(params), x0, y0, x1, y1, out.ctypes.data))
+        return out
+
+    def stats(self):
+        s = Stats()
+        _check(lib().drt_cuda_get_stats(self._h, C.byref(s)))
+        return s
+
+    def film_to_rgb(self, film, width, height, which, rgb_ptr=None, bgra_ptr=None, stream=None):
+        _check(lib().drt_cuda_film_to_rgb(self._h, C.byref(film), width, height, which, rgb_ptr, bgra_ptr, stream))
+
+    def film_merge(self, dst, src, width, height, stream=None):
+        _check(lib().drt_cuda_film_merge(self._h, C.byref(dst), C.byref(src), width, height, stream))
+
+    def measure_fp32_peak(self, packed=False):
+        v = C.c_double()
+        _check(lib().drt_cuda_measure_fp32_peak(self._h, int(packed), C.byref(v)))
+        return v.value
+
+
+def film_from_tensors(total, filt, mean, m2):
+    """drt_film over caller-owned torch CUDA tensors (f32, contiguous): PyTorch is only the allocator here."""
+    for t in (total, filt, mean, m2):
+        assert t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4
+    return Film(total.data_ptr(), filt.data_ptr(), mean.data_ptr(), m2.data_ptr())

@@ -1,0 +1,113 @@
+/*
+ * include/drt_cuda.h -- the drop-in boundary: a plain C ABI over the sm_100a render path.
+ *
+ * The reference has no plugin or FFI layer; its seams are C functions inside one translation unit
+ * (SURVEY.md 8b).  These entry points replace them one for one:
+ *
+ *   drt_cuda_render_*       <- render_image's sampling loop      src/daily_ray_trace.c:709-752
+ *                              (sample_scene :571-618, cast_ray :432-479, film + Welford :720-743)
+ *   drt_cuda_sample_paths   <- sample_scene per (x, y, sample)    src/daily_ray_trace.c:571 (the inner seam, :729)
+ *   drt_cuda_film_to_rgb    <- spd_file_to_rgb_f64_pixels         src/daily_ray_trace.c:1-28
+ *                              + spectrum_to_rgb_f64 src/spectrum.c:49-82 + rgb_f64_to_rgb_u8 src/win32_platform.c:136-147
+ *   drt_cuda_film_merge     <- (new) combines films of disjoint sample ranges: multi-GPU sample sharding
+ *   drt_cuda_upload_scene   <- load_scene's result (scene_data/camera_data, daily_ray_trace.h:146-170) + init_spd_tables
+ *
+ * Conventions: POD structs and raw pointers only (no C++/torch types); every call returns 0 or a negative
+ * DRT_CUDA_E_* code and drt_cuda_last_error() describes the failure; a context is bound to one CUDA device and
+ * may be driven by one host thread at a time.  There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Film layout (all planes f32, pixel-major, row-major from the film's bottom-left like the .spd files):
+ *   sum[W*H*N]  sum of path contributions        filter[W*H]  sum of filter weights (= sample count, Q20)
+ *   mean[W*H*N] Welford running mean             m2[W*H*N]    Welford sum of squared deviations (Q17)
+ */
+#ifndef DRT_CUDA_H
+#define DRT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "drt_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum
+{
+    DRT_CUDA_OK = 0,
+    DRT_CUDA_E_NO_DEVICE = -101,   /* no CUDA device / driver: the product path never falls back to the CPU */
+    DRT_CUDA_E_CUDA = -102,        /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+    DRT_CUDA_E_ARG = -103,
+    DRT_CUDA_E_UNSUPPORTED = -104, /* scene outside what the kernels handle (message says what) */
+    DRT_CUDA_E_STATE = -105        /* call order: render before upload_scene, ... */
+};
+
+typedef struct drt_cuda_context drt_cuda_context;
+
+/* arithmetic of the geometric part of a path (intersection, sampling, visibility) */
+enum { DRT_GEOMETRY_F32 = 0, DRT_GEOMETRY_F64 = 1 };
+
+typedef struct
+{
+    float *sum, *filter, *mean, *m2;   /* device pointers (render_device) or host pointers (render_host) */
+} drt_film;
+
+/* work counters of one render call: the R_c, R_s, B of the flops formula in SURVEY.md 8d */
+typedef struct
+{
+    uint64_t paths, closest_rays, shadow_rays, shaded_bounces, rng_draws;
+    uint64_t terminated_at_depth[8];
+    uint64_t reached_depth_cap;
+    uint64_t kernel_launches;          /* kernels of this library launched by the call */
+} drt_cuda_stats;
+
+const char *drt_cuda_last_error(void);
+int  drt_cuda_device_count(void);
+
+int  drt_cuda_create(int device, drt_cuda_context **out);
+void drt_cuda_destroy(drt_cuda_context *ctx);
+
+/* Copies scene, camera and tables to the device (f64 narrowed as the kernels need). */
+int  drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables);
+
+/* DRT_GEOMETRY_F32 (default) or DRT_GEOMETRY_F64; spectra and film are f32 in both. */
+int  drt_cuda_set_geometry_precision(drt_cuda_context *ctx, int precision);
+
+/* Bytes of one f32 film plane set for a W x H image with the uploaded scene's N wavelengths. */
+int  drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, uint32_t height, size_t *spectral_plane_bytes, size_t *filter_plane_bytes);
+
+/* Renders samples [sample_begin, sample_end) of every pixel into caller-owned DEVICE planes on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream).  accumulate=0 overwrites the planes; accumulate=1
+ * continues films that already hold earlier samples of the same pixels.  Asynchronous w.r.t. the host. */
+int  drt_cuda_render_device(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_device,
+                            int accumulate, void *stream);
+
+/* The same through HOST buffers: renders into library-owned device planes, then copies the four planes to
+ * `film_host` (pinned or pageable) and waits.  This is the end-to-end call the Linux main uses. */
+int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_host);
+
+/* Counters of the most recent render_* / sample_paths call (waits for it to finish). */
+int  drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out);
+
+/* Per-path spectral radiance, the sample_scene seam: for every pixel of the rectangle [x0,x1) x [y0,y1) and every
+ * sample in [params->sample_begin, sample_end) writes N f32 values to host buffer out[((y-y0)*(x1-x0)+(x-x0))*spp + s][N]. */
+int  drt_cuda_sample_paths(drt_cuda_context *ctx, const drt_render_params *params,
+                           uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, float *out_host);
+
+/* which = 0: sum/filter, 1: mean, 2: m2 divided by its per-pixel maximum (the three .bmp images of win32_main.c:150-152).
+ * rgb_device: 3 f32 per pixel (linear RGB, may be NULL); bgra_device: packed u32 per pixel (may be NULL). */
+int  drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film_device, uint32_t width, uint32_t height, int which,
+                          float *rgb_device, uint32_t *bgra_device, void *stream);
+
+/* dst <- dst (+) src for films over the same pixels and disjoint samples (Chan et al. merge of count/mean/M2,
+ * plain addition of sum/filter).  All device pointers; src may live on a peer GPU that this device can address. */
+int  drt_cuda_film_merge(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *src_device,
+                         uint32_t width, uint32_t height, void *stream);
+
+/* Measured FP32 FMA throughput of this device (TFLOP/s, FFMA counted as 2 flops): the roofline denominator
+ * MEASURED_PEAKS.json does not carry.  packed=1 uses fma.rn.f32x2. */
+int  drt_cuda_measure_fp32_peak(drt_cuda_context *ctx, int packed, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+"""GPU parity (the -m gpu tier): the CUDA path through the C ABI against the CPU oracle, RNG-matched per path.
+
+Tolerances: per (pixel, sample) the max-over-wavelength relative error must be <= 1e-3 (absolute floor
+1e-6 x the largest radiance) for >= 99.5 % of paths with f32 geometry; the rest are discrete-branch flips (a ray that
+lands the other side of an edge in f32) and are counted.  With f64 geometry the flips disappear, which is the evidence
+that they are branch flips and not arithmetic error."""
+import importlib
+
+import numpy as np
+import pytest
+
+import common
+import oracledriver
+
+cuda = importlib.import_module("daily-ray-trace_b200.cuda")
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3
+CASES = [
+    # scene, W, H, tile (x0,y0,x1,y1), spp, depth, scheme
+    ("cornell_plane_light", 64, 64, (0, 0, 64, 64), 4, 4, "pixel_random"),
+    ("init_cornell", 64, 48, (0, 0, 64, 48), 3, 4, "pixel_random"),
+    ("cornell_large_box", 48, 48, (8, 8, 40, 40), 33, 4, "pixel_random"),
+    ("cornell_downward", 48, 48, (0, 0, 48, 48), 2, 4, "pixel_random"),
+    ("first_scene", 32, 32, (0, 0, 32, 32), 2, 4, "pixel_center"),
+    ("example_scene", 32, 32, (0, 0, 32, 32), 1, 3, "pixel_random"),
+    ("stress_all", 64, 48, (0, 0, 64, 48), 5, 6, "pixel_random"),
+]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cuda.Context(0)
+    yield c
+    c.close()
+
+
+def _run(ctx, scene_name, w, h, tile, spp, depth, scheme, geometry, seed=0xC0FFEE):
+    cfg, tables, scene, camera = common.load(scene_name, w, h, spp, depth, scheme)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(geometry)
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, seed)
+    x0, y0, x1, y1 = tile
+    gpu = ctx.sample_paths(prm, x0, y0, x1, y1)
+    st = ctx.stats()
+    o_sum, o_avg, o_m2, o_paths, cnt = oracledriver.render_tile(scene, camera, prm, x0, y0, x1, y1, want_paths=True)
+    return gpu, o_paths, st, cnt
+
+
+@pytest.mark.parametrize("scene,w,h,tile,spp,depth,scheme", CASES)
+def test_per_path_radiance_f32(ctx, scene, w, h, tile, spp, depth, scheme):
+    gpu, ref, st, cnt = _run(ctx, scene, w, h, tile, spp, depth, scheme, cuda.GEOMETRY_F32)
+    err = common.path_errors(gpu, ref)
+    ok = (err <= REL_TOL).mean()
+    print(f"\n{scene}: {err.size} paths, within {REL_TOL:g}: {100 * ok:.3f} %, median err {np.median(err):.2e}, "
+          f"p99 {np.quantile(err, 0.99):.2e}, mismatching {int((err > REL_TOL).sum())}")
+    assert ok >= 0.995
+    assert st.paths == cnt.paths == err.size
+    # work counters agree with the oracle up to the few flipped paths
+    for a, b in ((st.closest_rays, cnt.closest_rays), (st.shadow_rays, cnt.shadow_rays), (st.rng_draws, cnt.rng_draws)):
+        assert abs(a - b) <= 0.01 * b + 8
+
+
+@pytest.mark.parametrize("scene,w,h,tile,spp,depth,scheme", CASES)
+def test_per_path_radiance_f64_geometry(ctx, scene, w, h, tile, spp, depth, scheme):
+    gpu, ref, st, cnt = _run(ctx, scene, w, h, tile, spp, depth, scheme, cuda.GEOMETRY_F64)
+    err = common.path_errors(gpu, ref)
+    ok = (err <= 1e-4).mean()
+    print(f"\n{scene} [f64 geometry]: within 1e-4: {100 * ok:.4f} %, max err {err.max():.2e}")
+    assert ok >= 0.9995
+    assert (st.closest_rays, st.shadow_rays, st.shaded_bounces) == (cnt.closest_rays, cnt.shadow_rays, cnt.shaded_bounces) or ok < 1.0
+
+
+def test_film_matches_oracle(ctx):
+    """Film planes (sum, filter, Welford mean and M2) through the host-buffer entry point."""
+    w, h, spp, depth = 48, 40, 37, 4
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, spp, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 99)
+    film = ctx.render_host(prm)
+    o_sum, o_avg, o_m2, _, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h)
+    n = scene.num_wavelengths
+    assert np.array_equal(film["filter"], o_sum[:, n].astype(np.float32))
+    scale = np.abs(o_sum[:, :n]).max()
+    bad_px = np.zeros(w * h, bool)
+    for name, ref in (("sum", o_sum[:, :n]), ("mean", o_avg), ("m2", o_m2)):
+        floor = 1e-5 * np.abs(ref).max()
+        rel = np.abs(film[name] - ref) / np.maximum(np.abs(ref), floor)
+        bad_px |= rel.max(axis=1) > 2e-3
+        print(f"\nfilm {name}: max rel {rel.max():.2e}, pixels over 2e-3: {(rel.max(axis=1) > 2e-3).sum()}")
+    assert bad_px.mean() <= 0.002
+    assert scale > 0
+
+
+def test_sample_ranges_compose(ctx):
+    """Rendering [0,a) then accumulating [a,b) equals rendering [0,b) (same per-path streams, same Welford order)."""
+    w, h, depth = 32, 32, 4
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, 48, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    import torch
+    n = scene.num_wavelengths
+
+    def planes():
+        return [torch.zeros(w * h * n, device="cuda"), torch.zeros(w * h, device="cuda"),
+                torch.zeros(w * h * n, device="cuda"), torch.zeros(w * h * n, device="cuda")]
+
+    a, b = planes(), planes()
+    ctx.render_device(oracledriver.params(w, h, 0, 48, depth, cfg.pixel_scheme, 5), cuda.film_from_tensors(*a))
+    ctx.render_device(oracledriver.params(w, h, 0, 20, depth, cfg.pixel_scheme, 5), cuda.film_from_tensors(*b))
+    ctx.render_device(oracledriver.params(w, h, 20, 48, depth, cfg.pixel_scheme, 5), cuda.film_from_tensors(*b), accumulate=True)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
