@@ -1,5 +1,8 @@
 import importlib, sys, time, ctypes as C
-sys.path.insert(0, "tests")
+import os
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+sys.path.insert(0, os.path.join(HERE, ".."))
 import common, oracledriver
 import torch
 cuda = importlib.import_module("daily-ray-trace_b200.cuda")
@@ -19,4 +22,4 @@ for scene, w, h, spp in [("cornell_plane_light", 1024, 1024, 64), ("init_cornell
         a.record(); ctx.render_device(prm, film); b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         st = ctx.stats()
-        print(f"{scene} geo={'f64' if geo else 'f32'} {w}x{h}x{spp}: {ms:.2f} ms  {w*h*spp/ms/1e6:.1f} Mpaths/s  rays/path {(st.closest_rays+st.shadow_rays)/st.paths:.2f}", flush=True)
+        print(f"{scene} geo={'f64' if geo else 'f32'} {w}x{h}x{spp}: {ms:.2f} ms  {w*h*spp/ms/1e3:.1f} Mpaths/s  rays/path {(st.closest_rays+st.shadow_rays)/st.paths:.2f}", flush=True)
