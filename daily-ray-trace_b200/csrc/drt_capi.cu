@@ -44,7 +44,7 @@ struct drt_cuda_context
     size_t smem_optin = 0;
     bool   have_scene = false;
     bool   f64_geometry = false;
-    int    n = 0, nslots = 0, nlights = 0;
+    int    n = 0, nslots = 0, nlights = 0, eval_words = 1;
     void  *d_geom32 = nullptr, *d_geom64 = nullptr;
     SpdIndex *d_index = nullptr;
     float *d_pool = nullptr;
@@ -56,6 +56,7 @@ struct drt_cuda_context
     float *d_film = nullptr; size_t film_bytes = 0;
     float *d_dump = nullptr; size_t dump_bytes = 0;
     uint64_t launches = 0;
+    size_t upload_bytes = 0;
     uint64_t last_launches = 0;
 };
 
@@ -147,6 +148,23 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         g->nlobes[m] = mm->num_lobes; g->dirf[m] = mm->dir_func;
         for(int k = 0; k < mm->num_lobes && k < DRT_MAX_LOBES; k += 1) g->lobes[m][k] = (unsigned char)mm->lobes[k];
         g->shin[m] = (R)mm->shininess; g->rough[m] = (R)mm->roughness;
+        /* which spectral bases this lobe list can produce, and how many record words one evaluation needs */
+        int mask = 0;
+        for(int k = 0; k < mm->num_lobes && k < DRT_MAX_LOBES; k += 1)
+            switch(mm->lobes[k])
+            {
+                case DRT_LOBE_BP_DIFFUSE: mask |= 1 << BK_DIFFUSE; break;
+                case DRT_LOBE_BP_GLOSSY: mask |= 1 << BK_GLOSSY; break;
+                case DRT_LOBE_MIRROR: mask |= 1 << BK_MIRROR; break;
+                case DRT_LOBE_FS_CONDUCTOR: mask |= 1 << BK_COND_ON; break;
+                case DRT_LOBE_FS_DIELECTRIC_REFLECTANCE: mask |= 1 << BK_DIEL_R; break;
+                case DRT_LOBE_FS_DIELECTRIC_TRANSMITTANCE: mask |= (1 << BK_DIEL_R) | (1 << BK_CONST); break;
+                case DRT_LOBE_CT_CONDUCTOR: mask |= 1 << BK_COND_MN; break;
+                default: break;
+            }
+        g->bmask[m] = mask;
+        int words = __builtin_popcount((unsigned)mask) + ((mask >> BK_COND_MN) & 1);
+        if(!mm->is_black_body && words > g->eval_words) g->eval_words = words;
         if(mm->spd_mask & (1 << DRT_SPD_REFRACT))
         {
             g->n630[m] = (R)value_at_wl(s, mm->spd[DRT_SPD_REFRACT], DRT_TRANS_WL);
@@ -218,10 +236,19 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_rgb_tables, rgbt.data(), rgbt.size(), cudaMemcpyHostToDevice);
     int nlights = g32->nlights;
+    int eval_words = g32->eval_words > 0 ? g32->eval_words : 1;
     delete g32; delete g64;
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "scene upload: %s", cudaGetErrorString(e));
-    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->pool_words = (uint32_t)pool.size();
+    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->eval_words = eval_words; ctx->pool_words = (uint32_t)pool.size();
+    ctx->upload_bytes = sizeof(GeomT<float>) + sizeof(GeomT<double>) + sizeof(SpdIndex) + pool.size() * 4 + rgbt.size();
     ctx->have_scene = true;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_scene_upload_bytes(const drt_cuda_context *ctx, size_t *bytes)
+{
+    if(!ctx || !bytes) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    *bytes = ctx->upload_bytes;
     return DRT_CUDA_OK;
 }
 
@@ -258,7 +285,8 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
     uint32_t spp = p->sample_end - p->sample_begin;
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
-    L.bounce_words = 3 + 9 * (uint32_t)ctx->nlights + 8;
+    L.eval_words = (uint32_t)ctx->eval_words;
+    L.bounce_words = 2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words;
     L.path_words = 2 + p->max_depth * L.bounce_words;
     /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
     int warps = DRT_CTA_WARPS;

@@ -17,14 +17,15 @@
 #define DRT_CTA_WARPS 8
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 
-/* spectral basis kinds a BSDF evaluation is expressed in (see eval_weights in drt_kernels.cu) */
+/* Spectral basis a BSDF evaluation is expressed in (eval_weights in drt_kernels.cu).  A material's lobe list fixes
+ * which of the seven can ever be non-zero (bmask); only those weights are stored in a path record, in this order,
+ * followed by the micro-normal cosine when BK_COND_MN is present. */
 enum { BK_CONST = 0, BK_DIFFUSE, BK_GLOSSY, BK_MIRROR, BK_DIEL_R, BK_COND_ON, BK_COND_MN, BK_COUNT };
-#define EVAL_WORDS (BK_COUNT + 1)  /* 7 weights + the micro-normal cosine of BK_COND_MN */
 
 template <typename R>
 struct GeomT
 {
-    int nsurf, nlights, base_mat, escape_mat, nmat, n, pad0, pad1;
+    int nsurf, nlights, base_mat, escape_mat, nmat, n, eval_words, pad1;
     R   trans_num, trans_den;      /* (630 - w0), (w1 - w0) of value_at_wl, spectrum.c:150-162 */
     int type[DRT_MAX_SURFACES], mat[DRT_MAX_SURFACES], light_surf[DRT_MAX_SURFACES];
     R   px[DRT_MAX_SURFACES], py[DRT_MAX_SURFACES], pz[DRT_MAX_SURFACES], rad[DRT_MAX_SURFACES];
@@ -36,6 +37,7 @@ struct GeomT
     R   light_pdf[DRT_MAX_SURFACES];
     /* materials */
     int mflags[DRT_MAX_MATERIALS];   /* bit0 is_black_body, bit1 is_emissive */
+    int bmask[DRT_MAX_MATERIALS];    /* bit k: basis kind k can be produced by this material's lobe list */
     int nlobes[DRT_MAX_MATERIALS], dirf[DRT_MAX_MATERIALS];
     unsigned char lobes[DRT_MAX_MATERIALS][DRT_MAX_LOBES];
     R   shin[DRT_MAX_MATERIALS], rough[DRT_MAX_MATERIALS];
@@ -62,6 +64,13 @@ struct DeviceStats
     unsigned long long reached_depth_cap;
 };
 
+/* Path record in shared memory, one column per path slot (word w of slot s at rec[w*32 + s]):
+ *   word 0            number of bounce records
+ *   word 1            vignette factor
+ *   per bounce        [0] header: kind(2) | surface material(5) | media swapped(1) | light visibility mask(16)
+ *                     [1] on_dot
+ *                     nlights x { eval weights (eval_words), light scale k }      next-event estimation
+ *                     eval weights (eval_words)                                   sampled direction, x 1/pdf    */
 struct RenderLaunch
 {
     const void     *geom;          /* GeomT<float> or GeomT<double> in global memory */
@@ -80,7 +89,8 @@ struct RenderLaunch
     int32_t  accumulate;
     int32_t  nlights;
     uint32_t pixels_per_task;      /* contiguous rectangle pixels claimed per warp task */
-    uint32_t bounce_words;         /* record words per bounce = 3 + 9*nlights + 8 */
-    uint32_t path_words;           /* record words per path   = 2 + max_depth*bounce_words */
+    uint32_t eval_words;           /* stored weights per BSDF evaluation (scene-wide maximum) */
+    uint32_t bounce_words;         /* 2 + nlights*(eval_words+1) + eval_words */
+    uint32_t path_words;           /* 2 + max_depth*bounce_words */
     uint32_t geom_bytes, pool_words;
 };

@@ -44,10 +44,12 @@ __device__ __forceinline__ float  r_sqrt(float x)  { return sqrtf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float  r_abs(float x)   { return fabsf(x); }
 __device__ __forceinline__ double r_abs(double x)  { return fabs(x); }
-__device__ __forceinline__ float  r_pow(float x, float y)   { return powf(x, y); }
-__device__ __forceinline__ double r_pow(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ void   r_sincos(float t, float *s, float *c)    { sincosf(t, s, c); }
-__device__ __forceinline__ void   r_sincos(double t, double *s, double *c) { sincos(t, s, c); }
+/* The transcendental library routines are large; one out-of-line copy each keeps the kernel inside the instruction cache. */
+__device__ __noinline__ float  r_pow(float x, float y)   { return powf(x, y); }
+__device__ __noinline__ double r_pow(double x, double y) { return pow(x, y); }
+/* sin and cos of pi*t: the reference's angles are all multiples of pi (2*pi*v, pi/4*ratio, rng.c:18,40-46) */
+__device__ __noinline__ void r_sincospi(float t, float *s, float *c)    { sincospif(t, s, c); }
+__device__ __noinline__ void r_sincospi(double t, double *s, double *c) { sincos(3.14159265358979323846 * t, s, c); }
 
 template <typename R> struct Num;
 template <> struct Num<float>
@@ -102,20 +104,28 @@ template <typename R> __device__ __forceinline__ V3<R> rotate_from_z(V3<R> n, V3
 
 /* ------------------------------------------------------------------ per-path random stream (include/drt_rng.h) */
 
+__device__ __noinline__ uint4 philox_block(uint32_t block, uint32_t seed_lo, uint32_t seed_hi, uint32_t key0, uint32_t key1)
+{
+    uint32_t out[4];
+    drt_philox4x32_10(block, 0u, seed_lo, seed_hi, key0, key1, out);
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 struct Rng
 {
     uint32_t key0, key1, seed_lo, seed_hi, draws;
-    uint32_t buf[4];
+    uint4 buf;
     __device__ __forceinline__ void begin(uint64_t seed, uint32_t pixel, uint32_t sample)
     {
         key0 = pixel; key1 = sample; seed_lo = (uint32_t)seed; seed_hi = (uint32_t)(seed >> 32); draws = 0;
+        buf = make_uint4(0u, 0u, 0u, 0u);
     }
     __device__ __forceinline__ uint32_t next31()
     {
         uint32_t lane = draws & 3u;
-        if(lane == 0) drt_philox4x32_10(draws >> 2, 0u, seed_lo, seed_hi, key0, key1, buf);
+        if(lane == 0) buf = philox_block(draws >> 2, seed_lo, seed_hi, key0, key1);
         draws += 1;
-        uint32_t w = (lane == 0) ? buf[0] : (lane == 1) ? buf[1] : (lane == 2) ? buf[2] : buf[3];
+        uint32_t w = (lane == 0) ? buf.x : (lane == 1) ? buf.y : (lane == 2) ? buf.z : buf.w;
         return w >> 1;
     }
     template <typename R> __device__ __forceinline__ R unit() { return Num<R>::unit(next31()); }
@@ -123,19 +133,38 @@ struct Rng
 
 /* ------------------------------------------------------------------ K2: closest hit / any hit over the SoA scene */
 
-template <typename R> __device__ __forceinline__ R hit_sphere(V3<R> o, V3<R> d, V3<R> c, R r)   /* geometry.c:123-146 */
+/* line_sphere_intersection, geometry.c:123-146: smallest non-negative root of t^2 - b t + c = 0, else +inf. */
+__device__ __forceinline__ double hit_sphere(V3<double> o, V3<double> d, V3<double> c, double r)
 {
-    V3<R> co = o - c;
-    R b = R(-2) * dot(co, d);
-    R cc = dot(co, co) - r * r;
-    R disc = b * b - R(4) * cc;
-    if(disc < R(0)) return Num<R>::inf();
-    R sq = r_sqrt(disc);
-    R s0 = (b + sq) / R(2);
-    R s1 = (b - sq) / R(2);
-    if(s0 < R(0) && s1 < R(0)) return Num<R>::inf();
-    if(s0 >= R(0) && s1 < R(0)) return s0;
-    if(s1 >= R(0) && s0 < R(0)) return s1;
+    V3<double> co = o - c;
+    double b = -2.0 * dot(co, d);
+    double cc = dot(co, co) - r * r;
+    double disc = b * b - 4.0 * cc;
+    if(disc < 0.0) return Num<double>::inf();
+    double sq = sqrt(disc);
+    double s0 = (b + sq) / 2.0;
+    double s1 = (b - sq) / 2.0;
+    if(s0 < 0.0 && s1 < 0.0) return Num<double>::inf();
+    if(s0 >= 0.0 && s1 < 0.0) return s0;
+    if(s1 >= 0.0 && s0 < 0.0) return s1;
+    return (s0 <= s1) ? s0 : s1;
+}
+/* The same roots in f32.  b^2 - 4c loses |o-c|^2 * eps, which near a silhouette (and for the reference's shadow test
+ * against the light's own sphere, margin 1e-4) decides hit or miss; the quarter discriminant r^2 - |co - (co.d) d|^2
+ * is the same quantity with error ~ r^2 * eps (Haines et al., Ray Tracing Gems ch. 7). */
+__device__ __forceinline__ float hit_sphere(V3<float> o, V3<float> d, V3<float> c, float r)
+{
+    V3<float> co = o - c;
+    float half_b = -dot(co, d);                 /* = b / 2 */
+    V3<float> perp = co + d * half_b;           /* component of co perpendicular to the ray */
+    float qdisc = r * r - dot(perp, perp);      /* = disc / 4 */
+    if(qdisc < 0.f) return Num<float>::inf();
+    float sq = sqrtf(qdisc);
+    float s0 = half_b + sq;
+    float s1 = half_b - sq;
+    if(s0 < 0.f && s1 < 0.f) return Num<float>::inf();
+    if(s0 >= 0.f && s1 < 0.f) return s0;
+    if(s1 >= 0.f && s0 < 0.f) return s1;
     return (s0 <= s1) ? s0 : s1;
 }
 
@@ -153,10 +182,24 @@ template <typename R> __device__ __forceinline__ R hit_plane(const GeomT<R> &g, 
     return inside ? l : Num<R>::inf();
 }
 
-template <typename R> __device__ __forceinline__ R hit_surface(const GeomT<R> &g, int i, V3<R> o, V3<R> d)
+/* Nearest surface strictly closer than `limit` along the ray, or -1 (the loops of find_ray_intersection
+ * daily_ray_trace.c:340-364 and points_mutually_visible :246-268; points are skipped, strict < keeps the lowest index
+ * on ties).  One shared out-of-line body serves closest-hit (limit = inf) and shadow rays (limit = vis_dist). */
+template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, R *dist_out)
 {
-    if(g.type[i] == DRT_GEO_SPHERE) return hit_sphere<R>(o, d, mk<R>(g.px[i], g.py[i], g.pz[i]), g.rad[i]);
-    return hit_plane<R>(g, i, o, d);
+    R best = limit;
+    int found = -1;
+    for(int i = 0; i < g.nsurf; i += 1)
+    {
+        int t = g.type[i];
+        R dist;
+        if(t == DRT_GEO_SPHERE) dist = hit_sphere(o, d, mk<R>(g.px[i], g.py[i], g.pz[i]), g.rad[i]);
+        else if(t == DRT_GEO_PLANE) dist = hit_plane<R>(g, i, o, d);
+        else continue;
+        if(dist < best) { best = dist; found = i; }
+    }
+    *dist_out = best;
+    return found;
 }
 
 template <typename R> struct Hit
@@ -169,16 +212,9 @@ template <typename R> struct Hit
 /* find_ray_intersection, daily_ray_trace.c:334-403.  Returns false on a miss (escape material). */
 template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R> &g, V3<R> o, V3<R> d, Hit<R> &h)
 {
-    R best = Num<R>::inf();
-    int found = -1;
     o = o + d * Num<R>::fudge();   /* Q2 */
-    for(int i = 0; i < g.nsurf; i += 1)
-    {
-        int t = g.type[i];
-        if(t != DRT_GEO_SPHERE && t != DRT_GEO_PLANE) continue;
-        R dist = hit_surface<R>(g, i, o, d);
-        if(dist < best) { best = dist; found = i; }   /* strict <: lowest index wins ties */
-    }
+    R best;
+    int found = nearest_surface<R>(g, o, d, Num<R>::inf(), &best);
     if(found < 0) return false;
     h.pos = o + d * best;
     V3<R> n = mk<R>(g.nx[found], g.ny[found], g.nz[found]);
@@ -205,13 +241,8 @@ template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g,
     V3<R> o = p0 + dir * Num<R>::fudge();
     V3<R> po = p1 - o;
     R vis_dist = r_sqrt(dot(po, po)) - Num<R>::fudge();
-    for(int i = 0; i < g.nsurf; i += 1)
-    {
-        int t = g.type[i];
-        if(t != DRT_GEO_SPHERE && t != DRT_GEO_PLANE) continue;
-        if(hit_surface<R>(g, i, o, dir) < vis_dist) return false;
-    }
-    return true;
+    R t;
+    return nearest_surface<R>(g, o, dir, vis_dist, &t) < 0;
 }
 
 /* ------------------------------------------------------------------ BSDF evaluation reduced to basis weights
@@ -219,16 +250,17 @@ template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g,
  * bdsf() (daily_ray_trace.c:215-229) sums the material's lobes through ONE scratch spectrum that is zeroed once;
  * lobes that "do not write" leave the previous lobe's value in it (Q7).  Every lobe output is a scalar times one of
  * seven spectra: 1, diffuse, glossy, mirror, R_dielectric(on_dot), F_conductor(on_dot), F_conductor(mn_dot).  Walking
- * the lobe list with a 7-vector as the scratch reproduces the sum, stale values included, as 7 weights. */
+ * the lobe list with a 7-vector as the scratch reproduces the sum, stale values included, as 7 weights.  The weights
+ * the material can produce (g.bmask) are stored to the record column `rec` (already offset to the slot) from word `at`. */
 template <typename R>
-__device__ __forceinline__ void eval_weights(const GeomT<R> &g, const Hit<R> &h, V3<R> in, bool is_reflection, bool is_transmission,
-                                             float scale, float w[EVAL_WORDS])
+__device__ __noinline__ void eval_weights(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in, int match, float scale,
+                                          float *rec, uint32_t at)
 {
+    const bool is_reflection = match & 1, is_transmission = match & 2;
     float cur[BK_COUNT], acc[BK_COUNT];
 #pragma unroll
     for(int k = 0; k < BK_COUNT; k += 1) { cur[k] = 0.f; acc[k] = 0.f; }
     float mn_cos = 0.f;
-    int m = h.surf_mat;
     int nl = g.nlobes[m];
     for(int li = 0; li < nl; li += 1)
     {
@@ -239,14 +271,14 @@ __device__ __forceinline__ void eval_weights(const GeomT<R> &g, const Hit<R> &h,
         switch(lobe)
         {
             case DRT_LOBE_BP_DIFFUSE:   /* bdsf.c:105-109 */
-                kind = BK_DIFFUSE; val = (float)((R(1) / Num<R>::pi()) * r_abs(dot(h.nrm, in)));
+                kind = BK_DIFFUSE; val = (float)((R(1) / Num<R>::pi()) * r_abs(dot(nrm, in)));
                 break;
             case DRT_LOBE_BP_GLOSSY:   /* bdsf.c:111-119 */
             {
-                V3<R> bis = normalise(h.out + in);
-                R nb = dot(h.nrm, bis);
+                V3<R> bis = normalise(out + in);
+                R nb = dot(nrm, bis);
                 R coef = r_pow((R(0) > nb) ? R(0) : nb, g.shin[m]);
-                kind = BK_GLOSSY; val = (float)(coef * r_abs(dot(h.nrm, in)));
+                kind = BK_GLOSSY; val = (float)(coef * r_abs(dot(nrm, in)));
                 break;
             }
             case DRT_LOBE_MIRROR:   /* bdsf.c:121-132: zero on mismatch */
@@ -263,24 +295,24 @@ __device__ __forceinline__ void eval_weights(const GeomT<R> &g, const Hit<R> &h,
                 break;
             case DRT_LOBE_CT_CONDUCTOR:   /* bdsf.c:174-186 */
             {
-                V3<R> mn = normalise(h.out + in);
-                R mn_dot = r_abs(dot(h.nrm, mn));
+                V3<R> mn = normalise(out + in);
+                R mn_dot = r_abs(dot(nrm, mn));
                 /* ggx_att(out, n, mn, rough) * 1/(4 on_dot), bdsf.c:3-42 */
                 R rough = g.rough[m], r2 = rough * rough;
-                R d = dot(h.nrm, mn), gg = R(0);
+                R d = dot(nrm, mn), gg = R(0);
                 if(d > R(0))
                 {
                     R d2 = d * d, d4 = d2 * d2, tan_sq = (R(1) / d2) - R(1);
                     gg = r2 / (Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
                 }
-                R v_mn = dot(h.out, mn), v_sn = dot(h.out, h.nrm);
+                R v_mn = dot(out, mn), v_sn = dot(out, nrm);
                 R quot = r_abs(v_mn / v_sn), att = R(0);
                 if(!(quot <= R(0)))
                 {
                     R tan_sq = (R(1) / (v_sn * v_sn)) - R(1);
                     att = R(2) / (R(1) + r_sqrt(R(1) + r2 * tan_sq));
                 }
-                kind = BK_COND_MN; val = (float)((gg * att) * (R(1) / (R(4) * h.on_dot)));
+                kind = BK_COND_MN; val = (float)((gg * att) * (R(1) / (R(4) * on_dot)));
                 mn_cos = (float)mn_dot;
                 break;
             }
@@ -289,17 +321,17 @@ __device__ __forceinline__ void eval_weights(const GeomT<R> &g, const Hit<R> &h,
         if(wrote)
         {
 #pragma unroll
-            for(int k = 0; k < BK_COUNT; k += 1) cur[k] = 0.f;
-#pragma unroll
-            for(int k = 0; k < BK_COUNT; k += 1) if(k == kind) cur[k] = val;
+            for(int k = 0; k < BK_COUNT; k += 1) cur[k] = (k == kind) ? val : 0.f;
             cur[BK_CONST] += val_const;
         }
 #pragma unroll
         for(int k = 0; k < BK_COUNT; k += 1) acc[k] += cur[k];
     }
+    const int mask = g.bmask[m];
 #pragma unroll
-    for(int k = 0; k < BK_COUNT; k += 1) w[k] = acc[k] * scale;
-    w[BK_COUNT] = mn_cos;
+    for(int k = 0; k < BK_COUNT; k += 1)
+        if(mask & (1 << k)) { rec[at * DRT_WARP] = acc[k] * scale; at += 1; }
+    if(mask & (1 << BK_COND_MN)) rec[at * DRT_WARP] = mn_cos;
 }
 
 /* dielectric Fresnel at one wavelength, bdsf.c:44-66 (Q9 kept) */
@@ -342,20 +374,20 @@ template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /
     R ry = rng.unit<R>();
     R ox = R(2) * rx - R(1), oy = R(2) * ry - R(1);
     if(ox == R(0) && oy == R(0)) return mk<R>(R(0), R(0), R(0));
-    R r, t;
-    if(r_abs(ox) > r_abs(oy)) { r = ox; t = (Num<R>::pi() / R(4)) * (oy / ox); }
-    else                      { r = oy; t = (Num<R>::pi() / R(2)) - (Num<R>::pi() / R(4)) * (ox / oy); }
+    R r, t;   /* t in units of pi */
+    if(r_abs(ox) > r_abs(oy)) { r = ox; t = R(0.25) * (oy / ox); }
+    else                      { r = oy; t = R(0.5) - R(0.25) * (ox / oy); }
     R s, c;
-    r_sincos(t, &s, &c);
+    r_sincospi(t, &s, &c);
     return mk<R>(r * c, r * s, R(0));
 }
 
+/* match: bit0 = `in` came out of the reflection formula, bit1 = out of the refraction formula (Q8) */
 template <typename R>
-__device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R> &h, Rng &rng, V3<R> &in, R &inv_pdf,
-                                                 bool &is_reflection, bool &is_transmission)
+__device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R> &h, Rng &rng, V3<R> &in, R &inv_pdf, int &match)
 {
     int m = h.surf_mat;
-    is_reflection = false; is_transmission = false;
+    match = 0;
     in = mk<R>(R(0), R(0), R(0)); inv_pdf = R(0);
     switch(g.dirf[m])
     {
@@ -365,7 +397,7 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
             R v = rng.unit<R>();
             R r = r_sqrt(R(1) - u * u);
             R s, c;
-            r_sincos(R(2) * Num<R>::pi() * v, &s, &c);
+            r_sincospi(R(2) * v, &s, &c);
             in = rotate_from_z<R>(h.nrm, mk<R>(r * c, r * s, u));
             inv_pdf = R(2) * Num<R>::pi();
             break;
@@ -386,12 +418,12 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
         case DRT_DIR_SPECULAR:   /* :215-220 */
             in = reflect<R>(neg(h.out), h.nrm);
             inv_pdf = R(1);
-            is_reflection = true;
+            match = 1;
             break;
         case DRT_DIR_TRANSMIT:   /* :222-234 */
             in = transmit<R>(neg(h.out), h.nrm, g.n630[h.inc_mat], g.n630[h.trans_mat]);
             inv_pdf = R(1);
-            is_transmission = (in.x == in.x) && (in.y == in.y) && (in.z == in.z);
+            match = ((in.x == in.x) && (in.y == in.y) && (in.z == in.z)) ? 2 : 0;
             break;
         case DRT_DIR_REFLECT_OR_TRANSMIT:   /* :236-259: reflect with probability R(630 nm) */
         {
@@ -403,13 +435,13 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
             {
                 in = reflect<R>(neg(h.out), h.nrm);
                 inv_pdf = R(1) / rd;
-                is_reflection = true;
+                match = 1;
             }
             else
             {
                 in = transmit<R>(neg(h.out), h.nrm, g.n630[h.inc_mat], g.n630[h.trans_mat]);
                 inv_pdf = R(1) / (R(1) - rd);
-                is_transmission = (in.x == in.x) && (in.y == in.y) && (in.z == in.z);
+                match = ((in.x == in.x) && (in.y == in.y) && (in.z == in.z)) ? 2 : 0;
             }
             break;
         }
@@ -424,7 +456,7 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
                 R cos_mn = R(1) / r_sqrt(R(1) + tan_mn * tan_mn);
                 R sin_mn = r_sqrt(R(1) - cos_mn * cos_mn);
                 R s, c;
-                r_sincos(R(2) * Num<R>::pi() * gq, &s, &c);
+                r_sincospi(R(2) * gq, &s, &c);
                 V3<R> mn = rotate_from_z<R>(h.nrm, mk<R>(sin_mn * c, sin_mn * s, cos_mn));
                 R sn_mn = dot(h.nrm, mn);
                 if(sn_mn < R(0)) { mn = neg(mn); sn_mn = -sn_mn; }
@@ -446,7 +478,7 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
     }
 }
 
-/* ------------------------------------------------------------------ path records in shared memory (SoA per warp) */
+/* ------------------------------------------------------------------ path records in shared memory */
 
 #define REC_NB   0
 #define REC_VIG  1
@@ -454,12 +486,11 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 #define KIND_SHADE 1u
 #define KIND_EMIT  2u
 
-__device__ __forceinline__ float &rec_at(float *rec, uint32_t field, uint32_t slot) { return rec[field * DRT_WARP + slot]; }
-
-/* ------------------------------------------------------------------ phase 1: trace one path, emit its record */
+/* ------------------------------------------------------------------ phase 1: trace one path, emit its record
+ * `rec` points at this lane's column (word w at rec[w*32]).  Returns the termination-histogram bin. */
 
 template <typename R>
-__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLaunch &L, float *rec, uint32_t slot,
+__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLaunch &L, float *rec,
                                                uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
 {
     Rng rng;
@@ -493,10 +524,10 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
         o = point;
         d = normalise(ap - o);   /* Q1 */
     }
-    rec_at(rec, REC_VIG, slot) = (float)dot(d, fwd);   /* Q20 */
+    rec[REC_VIG * DRT_WARP] = (float)dot(d, fwd);   /* Q20 */
 
     uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth;
-    const uint32_t bw = L.bounce_words;
+    const uint32_t bw = L.bounce_words, ew = L.eval_words;
     for(uint32_t depth = 0; depth < L.max_depth; depth += 1)
     {
         Hit<R> h;
@@ -509,7 +540,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
         {
             if(flags & 2)
             {
-                rec_at(rec, base, slot) = __uint_as_float(KIND_EMIT | ((uint32_t)m << 2));   /* Q6 */
+                rec[base * DRT_WARP] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 2));   /* Q6 */
                 nb += 1;
             }
             end_depth = depth;
@@ -536,7 +567,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
                 R v = rng.unit<R>();
                 R r = r_sqrt(R(1) - u * u);
                 R s, c;
-                r_sincos(R(2) * Num<R>::pi() * v, &s, &c);
+                r_sincospi(R(2) * v, &s, &c);
                 lp = lp + mk<R>(r * c, r * s, u) * g.rad[ls];   /* Q5 */
                 k = g.light_pdf[ls];
             }
@@ -550,132 +581,151 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
             shadow += 1;
             if(visible<R>(g, h.pos, lp))
             {
-                float w[EVAL_WORDS];
-                eval_weights<R>(g, h, normalise(lp - h.pos), false, false, 1.f, w);
-                uint32_t e = base + 3 + 9 * (uint32_t)j;
-#pragma unroll
-                for(int q = 0; q < EVAL_WORDS; q += 1) rec_at(rec, e + q, slot) = w[q];
-                rec_at(rec, e + 8, slot) = (float)k;
+                uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+                eval_weights<R>(g, h.surf_mat, h.nrm, h.out, h.on_dot, normalise(lp - h.pos), 0, 1.f, rec, e);
+                rec[(e + ew) * DRT_WARP] = (float)k;
                 vis_mask |= 1u << j;
             }
         }
         /* K4: sample the next direction and evaluate the BSDF for it, cast_ray :464-472 */
-        V3<R> in; R inv_pdf; bool is_refl, is_trans;
-        sample_direction<R>(g, h, rng, in, inv_pdf, is_refl, is_trans);
-        {
-            float w[EVAL_WORDS];
-            eval_weights<R>(g, h, in, is_refl, is_trans, (float)inv_pdf, w);
-            uint32_t e = base + 3 + 9 * (uint32_t)g.nlights;
-#pragma unroll
-            for(int q = 0; q < EVAL_WORDS; q += 1) rec_at(rec, e + q, slot) = w[q];
-        }
-        rec_at(rec, base + 0, slot) = __uint_as_float(KIND_SHADE | ((uint32_t)h.surf_mat << 2) | ((uint32_t)h.inc_mat << 7) | ((uint32_t)h.trans_mat << 12));
-        rec_at(rec, base + 1, slot) = __uint_as_float(vis_mask);
-        rec_at(rec, base + 2, slot) = (float)h.on_dot;
+        V3<R> in; R inv_pdf; int match;
+        sample_direction<R>(g, h, rng, in, inv_pdf, match);
+        eval_weights<R>(g, h.surf_mat, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, base + 2 + (ew + 1) * (uint32_t)g.nlights);
+        uint32_t swapped = (h.inc_mat != g.base_mat) ? 1u : 0u;
+        rec[base * DRT_WARP] = __uint_as_float(KIND_SHADE | ((uint32_t)h.surf_mat << 2) | (swapped << 7) | (vis_mask << 8));
+        rec[(base + 1) * DRT_WARP] = (float)h.on_dot;
         nb += 1;
         d = in;
         o = h.pos;
     }
-    rec_at(rec, REC_NB, slot) = __uint_as_float(nb);
-
+    rec[REC_NB * DRT_WARP] = __uint_as_float(nb);
     tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
     return (end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8;   /* histogram bin: depth of termination, 8 = hit the cap */
 }
 
 /* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp */
 
+/* One BSDF evaluation expanded over this lane's wavelengths.  `mask` (the material's basis set) is warp-uniform, so
+ * every branch below is uniform; d_row/g_row are the material's diffuse/glossy rows already in registers. */
 template <int NS>
-__device__ __forceinline__ void eval_spectrum(const float *rec, uint32_t e, uint32_t slot, const SpdIndex &ix, const float *pool,
-                                              int surf_mat, int inc_mat, int trans_mat, float on_dot, uint32_t lane,
+__device__ __forceinline__ void eval_spectrum(const float *col, uint32_t at, int mask, const float (&d_row)[NS], const float (&g_row)[NS],
+                                              const SpdIndex &ix, const float *pool_lane, int surf_mat, int inc_mat, int trans_mat, float on_dot,
                                               bool &have_r, float (&rl)[NS], bool &have_f, float (&fl)[NS], float (&f)[NS])
 {
-    float w[EVAL_WORDS];
-#pragma unroll
-    for(int q = 0; q < EVAL_WORDS; q += 1) w[q] = rec[(e + q) * DRT_WARP + slot];
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) f[k] = w[BK_CONST];
-    if(w[BK_DIFFUSE] != 0.f)
+    if(mask == ((1 << BK_DIFFUSE) | (1 << BK_GLOSSY)))   /* the Blinn-Phong plastic of every shipped wall */
     {
-        const float *row = pool + ix.row[surf_mat][DRT_SPD_DIFFUSE] * ix.npad + lane;
+        float wd = col[at * DRT_WARP], wg = col[(at + 1) * DRT_WARP];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_DIFFUSE], row[k * DRT_WARP], f[k]);
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(wg, g_row[k], wd * d_row[k]);
+        return;
     }
-    if(w[BK_GLOSSY] != 0.f)
-    {
-        const float *row = pool + ix.row[surf_mat][DRT_SPD_GLOSSY] * ix.npad + lane;
+    float base = 0.f;
+    if(mask & (1 << BK_CONST)) { base = col[at * DRT_WARP]; at += 1; }
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_GLOSSY], row[k * DRT_WARP], f[k]);
-    }
-    if(w[BK_MIRROR] != 0.f)
+    for(int k = 0; k < NS; k += 1) f[k] = base;
+    if(mask & (1 << BK_DIFFUSE))
     {
-        const float *row = pool + ix.row[surf_mat][DRT_SPD_MIRROR] * ix.npad + lane;
+        float w = col[at * DRT_WARP]; at += 1;
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_MIRROR], row[k * DRT_WARP], f[k]);
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, d_row[k], f[k]);
     }
-    if(w[BK_DIEL_R] != 0.f)
+    if(mask & (1 << BK_GLOSSY))
     {
-        if(!have_r)
+        float w = col[at * DRT_WARP]; at += 1;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, g_row[k], f[k]);
+    }
+    if(mask & (1 << BK_MIRROR))
+    {
+        float w = col[at * DRT_WARP]; at += 1;
+        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR] * ix.npad;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
+    }
+    if(mask & (1 << BK_DIEL_R))
+    {
+        float w = col[at * DRT_WARP]; at += 1;
+        if(w != 0.f)
         {
-            const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
-            const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
+            if(!have_r)
+            {
+                const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
+                const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) rl[k] = fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot);
-            have_r = true;
+                for(int k = 0; k < NS; k += 1) rl[k] = fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot);
+                have_r = true;
+            }
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, rl[k], f[k]);
         }
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_DIEL_R], rl[k], f[k]);
     }
-    if(w[BK_COND_ON] != 0.f)
+    if(mask & (1 << BK_COND_ON))
     {
-        if(!have_f)
+        float w = col[at * DRT_WARP]; at += 1;
+        if(w != 0.f)
         {
-            const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
-            const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
-            const float *te = pool + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad + lane;
+            if(!have_f)
+            {
+                const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
+                const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
+                const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) fl[k] = fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot);
-            have_f = true;
+                for(int k = 0; k < NS; k += 1) fl[k] = fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot);
+                have_f = true;
+            }
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fl[k], f[k]);
         }
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w[BK_COND_ON], fl[k], f[k]);
     }
-    if(w[BK_COND_MN] != 0.f)
+    if(mask & (1 << BK_COND_MN))
     {
-        const float *ir = pool + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad + lane;
-        const float *tr = pool + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad + lane;
-        const float *te = pool + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad + lane;
+        float w = col[at * DRT_WARP], mn_cos = col[(at + 1) * DRT_WARP];
+        if(w != 0.f)
+        {
+            const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
+            const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
+            const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad;
 #pragma unroll
-        for(int k = 0; k < NS; k += 1)
-            f[k] = fmaf(w[BK_COND_MN], fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], w[BK_COUNT]), f[k]);
+            for(int k = 0; k < NS; k += 1)
+                f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], mn_cos), f[k]);
+        }
     }
 }
 
-/* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from the record; returns the path contribution
- * already multiplied by the vignette factor (:612-615). */
+/* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from record column `col` (nb >= 1 bounces);
+ * returns the path contribution already multiplied by the vignette factor (:612-615). */
 template <int NS, typename G>
-__device__ __forceinline__ void replay_path(const float *rec, uint32_t slot, const G &g, const SpdIndex &ix, const float *pool,
-                                            const RenderLaunch &L, uint32_t lane, float (&c)[NS])
+__device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool_lane,
+                                            const RenderLaunch &L, float (&c)[NS])
 {
     float thr[NS], dst[NS];
 #pragma unroll
     for(int k = 0; k < NS; k += 1) { thr[k] = 1.f; dst[k] = 0.f; }
-    uint32_t nb = __float_as_uint(rec[REC_NB * DRT_WARP + slot]);
-    const uint32_t bw = L.bounce_words;
+    const uint32_t bw = L.bounce_words, ew = L.eval_words;
     for(uint32_t b = 0; b < nb; b += 1)
     {
         uint32_t base = REC_HEAD + b * bw;
-        uint32_t hdr = __float_as_uint(rec[base * DRT_WARP + slot]);
+        uint32_t hdr = __float_as_uint(col[base * DRT_WARP]);
         int surf_mat = (hdr >> 2) & 31;
         if((hdr & 3u) == KIND_EMIT)
         {
-            const float *row = pool + ix.row[surf_mat][DRT_SPD_EMISSION] * ix.npad + lane;
+            const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_EMISSION] * ix.npad;
 #pragma unroll
             for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], row[k * DRT_WARP], dst[k]);
             break;
         }
-        int inc_mat = (hdr >> 7) & 31, trans_mat = (hdr >> 12) & 31;
-        uint32_t vis = __float_as_uint(rec[(base + 1) * DRT_WARP + slot]);
-        float on_dot = rec[(base + 2) * DRT_WARP + slot];
+        const int mask = g.bmask[surf_mat];
+        const bool swapped = (hdr >> 7) & 1u;
+        const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
+        const uint32_t vis = hdr >> 8;
+        const float on_dot = col[(base + 1) * DRT_WARP];
+        float d_row[NS], g_row[NS];
+        {
+            const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE] * ix.npad;
+            const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY] * ix.npad;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_WARP]; g_row[k] = gr[k * DRT_WARP]; }
+        }
         bool have_r = false, have_f = false;
         float rl[NS], fl[NS], f[NS], contrib[NS];
 #pragma unroll
@@ -683,29 +733,95 @@ __device__ __forceinline__ void replay_path(const float *rec, uint32_t slot, con
         for(int j = 0; j < L.nlights; j += 1)
         {
             if(!((vis >> j) & 1u)) continue;
-            uint32_t e = base + 3 + 9 * (uint32_t)j;
-            eval_spectrum<NS>(rec, e, slot, ix, pool, surf_mat, inc_mat, trans_mat, on_dot, lane, have_r, rl, have_f, fl, f);
-            float kk = rec[(e + 8) * DRT_WARP + slot];
-            const float *erow = pool + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION] * ix.npad + lane;
+            uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+            eval_spectrum<NS>(col, e, mask, d_row, g_row, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, have_r, rl, have_f, fl, f);
+            float kk = col[(e + ew) * DRT_WARP];
+            const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION] * ix.npad;
 #pragma unroll
             for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
         }
 #pragma unroll
         for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], contrib[k], dst[k]);
-        eval_spectrum<NS>(rec, base + 3 + 9 * (uint32_t)L.nlights, slot, ix, pool, surf_mat, inc_mat, trans_mat, on_dot, lane,
-                          have_r, rl, have_f, fl, f);
+        eval_spectrum<NS>(col, base + 2 + (ew + 1) * (uint32_t)L.nlights, mask, d_row, g_row, ix, pool_lane, surf_mat, inc_mat, trans_mat,
+                          on_dot, have_r, rl, have_f, fl, f);
 #pragma unroll
         for(int k = 0; k < NS; k += 1) thr[k] *= f[k];
     }
-    float vig = rec[REC_VIG * DRT_WARP + slot];
+    float vig = col[REC_VIG * DRT_WARP];
 #pragma unroll
     for(int k = 0; k < NS; k += 1) c[k] = dst[k] * vig;
 }
 
+/* film of one pixel held by a warp: lane l owns wavelengths l, l+32, ... */
+template <int NS> struct PixelFilm
+{
+    float sum[NS], mean[NS], m2[NS], cnt;
+    bool  lit;      /* some sample of this pixel was non-zero (warp-uniform) */
+    __device__ __forceinline__ void clear()
+    {
+        cnt = 0.f; lit = false;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) { sum[k] = 0.f; mean[k] = 0.f; m2[k] = 0.f; }
+    }
+    __device__ __forceinline__ void load(const FilmPtrs &film, uint32_t gpix, uint32_t n, uint32_t lane)
+    {
+        cnt = film.filter[gpix]; lit = true;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            uint32_t wl = lane + k * DRT_WARP;
+            size_t at = (size_t)gpix * n + wl;
+            sum[k] = (wl < n) ? film.sum[at] : 0.f; mean[k] = (wl < n) ? film.mean[at] : 0.f; m2[k] = (wl < n) ? film.m2[at] : 0.f;
+        }
+    }
+    __device__ __forceinline__ void store(const FilmPtrs &film, uint32_t gpix, uint32_t n, uint32_t lane) const
+    {
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            uint32_t wl = lane + k * DRT_WARP;
+            if(wl < n)
+            {
+                size_t at = (size_t)gpix * n + wl;
+                film.sum[at] = sum[k]; film.mean[at] = mean[k]; film.m2[at] = m2[k];
+            }
+        }
+        if(lane == 0) film.filter[gpix] = cnt;
+    }
+    /* K6: film accumulation + Welford, daily_ray_trace.c:732-743 (filter weight is the constant 1, Q20) */
+    __device__ __forceinline__ void add(const float (&c)[NS])
+    {
+        cnt += 1.f; lit = true;
+        float inv = 1.f / cnt;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            sum[k] += c[k];
+            float delta = c[k] - mean[k];
+            mean[k] = fmaf(delta, inv, mean[k]);
+            m2[k] = fmaf(delta, c[k] - mean[k], m2[k]);
+        }
+    }
+    /* the same update for a path that contributed nothing: exact no-op on an all-zero pixel */
+    __device__ __forceinline__ void add_zero()
+    {
+        cnt += 1.f;
+        if(!lit) return;
+        float inv = 1.f / cnt;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            float delta = -mean[k];
+            mean[k] = fmaf(delta, inv, mean[k]);
+            m2[k] = fmaf(delta, -mean[k], m2[k]);
+        }
+    }
+};
+
 /* ------------------------------------------------------------------ the kernel */
 
 template <typename R, int NS>
-__global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const RenderLaunch L)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
@@ -735,10 +851,12 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const Render
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     float *rec = srec + (size_t)warp * L.path_words * DRT_WARP;
+    const float *pool_lane = spool + lane;
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
     const uint32_t n = (uint32_t)ix.n;
     const uint32_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+    const bool have_film = L.film.sum != nullptr;
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
     uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
@@ -748,23 +866,27 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const Render
         if(lane == 0) task = atomicAdd(L.task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if(task >= ntasks) break;
-        uint32_t p_begin = task * L.pixels_per_task;
-        uint32_t p_end = min(p_begin + L.pixels_per_task, npix);
-        uint32_t total = (p_end - p_begin) * spp;
+        const uint32_t p_begin = task * L.pixels_per_task;
+        const uint32_t p_end = min(p_begin + L.pixels_per_task, npix);
+        const uint32_t total = (p_end - p_begin) * spp;
         traced += total;
 
-        /* film of the pixel being accumulated, in registers: lane holds wavelengths lane, lane+32, ... */
-        float f_sum[NS], f_mean[NS], f_m2[NS], f_cnt = 0.f;
-        uint32_t cur_pixel = 0xffffffffu, cur_gpix = 0;
+        /* replay cursor: local pixel, its image coordinates, sample index inside the pixel */
+        uint32_t cur_lp = p_begin, cur_x = L.x0 + p_begin % rw, cur_y = L.y0 + p_begin / rw, cur_s = 0;
+        PixelFilm<NS> film;
+        film.clear();
+        if(L.accumulate && have_film) film.load(L.film, cur_y * L.width + cur_x, n, lane);
 
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
+            /* ---- phase 1: lane = path ---- */
             uint32_t q = q0 + lane;
             uint32_t bin = 9;
             if(q < total)
             {
-                uint32_t lp = p_begin + q / spp, s = L.sample_begin + q % spp;
-                bin = trace_path<R>(g, L, rec, lane, L.x0 + lp % rw, L.y0 + lp / rw, s, tally);
+                uint32_t lp = p_begin, s = q;
+                if(L.pixels_per_task > 1) { lp += q / spp; s = q % spp; }
+                bin = trace_path<R>(g, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
             }
             __syncwarp();
 #pragma unroll
@@ -773,59 +895,32 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const Render
                 uint32_t votes = __popc(__ballot_sync(0xffffffffu, bin == d));
                 if(lane == d) hist += votes;
             }
-            uint32_t count = min((uint32_t)DRT_WARP, total - q0);
+            /* ---- phase 2: lane = wavelength, paths in sample order ---- */
+            const uint32_t count = min((uint32_t)DRT_WARP, total - q0);
+            const uint32_t my_nb = __float_as_uint(rec[REC_NB * DRT_WARP + lane]);
             for(uint32_t slot = 0; slot < count; slot += 1)
             {
-                uint32_t qq = q0 + slot;
-                uint32_t lp = p_begin + qq / spp;
-                if(lp != cur_pixel)
+                if(cur_s == spp)   /* next pixel of the task (only when a task holds several pixels, spp < 32) */
                 {
-                    if(cur_pixel != 0xffffffffu && L.film.sum)
-                    {
-#pragma unroll
-                        for(int k = 0; k < NS; k += 1)
-                        {
-                            uint32_t wl = lane + k * DRT_WARP;
-                            if(wl < n)
-                            {
-                                size_t at = (size_t)cur_gpix * n + wl;
-                                L.film.sum[at] = f_sum[k]; L.film.mean[at] = f_mean[k]; L.film.m2[at] = f_m2[k];
-                            }
-                        }
-                        if(lane == 0) L.film.filter[cur_gpix] = f_cnt;
-                    }
-                    cur_pixel = lp;
-                    cur_gpix = (L.y0 + lp / rw) * L.width + (L.x0 + lp % rw);
-                    f_cnt = 0.f;
-#pragma unroll
-                    for(int k = 0; k < NS; k += 1) { f_sum[k] = 0.f; f_mean[k] = 0.f; f_m2[k] = 0.f; }
-                    if(L.accumulate && L.film.sum)
-                    {
-                        f_cnt = L.film.filter[cur_gpix];
-#pragma unroll
-                        for(int k = 0; k < NS; k += 1)
-                        {
-                            uint32_t wl = lane + k * DRT_WARP;
-                            if(wl < n)
-                            {
-                                size_t at = (size_t)cur_gpix * n + wl;
-                                f_sum[k] = L.film.sum[at]; f_mean[k] = L.film.mean[at]; f_m2[k] = L.film.m2[at];
-                            }
-                        }
-                    }
+                    if(have_film) film.store(L.film, cur_y * L.width + cur_x, n, lane);
+                    cur_lp += 1; cur_s = 0;
+                    cur_x += 1;
+                    if(cur_x == L.x1) { cur_x = L.x0; cur_y += 1; }
+                    film.clear();
+                    if(L.accumulate && have_film) film.load(L.film, cur_y * L.width + cur_x, n, lane);
                 }
+                const uint32_t nb = __shfl_sync(0xffffffffu, my_nb, slot);
                 float c[NS];
-                replay_path<NS>(rec, slot, g, ix, spool, L, lane, c);
-                /* K6: film accumulation + Welford, daily_ray_trace.c:732-743 (filter weight is the constant 1, Q20) */
-                f_cnt += 1.f;
-                float inv = 1.f / f_cnt;
-#pragma unroll
-                for(int k = 0; k < NS; k += 1)
+                if(nb == 0)
                 {
-                    f_sum[k] += c[k];
-                    float delta = c[k] - f_mean[k];
-                    f_mean[k] = fmaf(delta, inv, f_mean[k]);
-                    f_m2[k] = fmaf(delta, c[k] - f_mean[k], f_m2[k]);
+#pragma unroll
+                    for(int k = 0; k < NS; k += 1) c[k] = 0.f;
+                    film.add_zero();
+                }
+                else
+                {
+                    replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, c);
+                    film.add(c);
                 }
                 if(L.path_dump)
                 {
@@ -833,26 +928,14 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 1) render_kernel(const Render
                     for(int k = 0; k < NS; k += 1)
                     {
                         uint32_t wl = lane + k * DRT_WARP;
-                        if(wl < n) L.path_dump[((size_t)lp * spp + qq % spp) * n + wl] = c[k];
+                        if(wl < n) L.path_dump[((size_t)cur_lp * spp + cur_s) * n + wl] = c[k];
                     }
                 }
+                cur_s += 1;
             }
             __syncwarp();
         }
-        if(cur_pixel != 0xffffffffu && L.film.sum)
-        {
-#pragma unroll
-            for(int k = 0; k < NS; k += 1)
-            {
-                uint32_t wl = lane + k * DRT_WARP;
-                if(wl < n)
-                {
-                    size_t at = (size_t)cur_gpix * n + wl;
-                    L.film.sum[at] = f_sum[k]; L.film.mean[at] = f_mean[k]; L.film.m2[at] = f_m2[k];
-                }
-            }
-            if(lane == 0) L.film.filter[cur_gpix] = f_cnt;
-        }
+        if(have_film) film.store(L.film, cur_y * L.width + cur_x, n, lane);
     }
 
     /* work counters: one shared-memory atomic per warp per counter, then one global atomic per CTA per counter */
@@ -880,6 +963,8 @@ static cudaError_t launch_render_ns(const RenderLaunch &L, int nslots, int grid,
 {
 #define DRT_LAUNCH(NS) do { \
         cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if(e != cudaSuccess) return e; \
+        e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         if(e != cudaSuccess) return e; \
         drt::render_kernel<R, NS><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
     switch(nslots)

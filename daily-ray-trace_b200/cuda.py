@@ -13,7 +13,7 @@ from ._structs import Camera, RenderParams, Scene, Tables
 GEOMETRY_F32, GEOMETRY_F64 = 0, 1
 
 EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
-           "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
+           "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
            "drt_cuda_get_stats", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak"]
 
@@ -54,6 +54,7 @@ def lib():
         L.drt_cuda_destroy.argtypes = [C.c_void_p]
         L.drt_cuda_destroy.restype = None
         L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
+        L.drt_cuda_scene_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
         L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
@@ -100,6 +101,11 @@ class Context:
     def upload_scene(self, scene, camera, tables):
         _check(lib().drt_cuda_upload_scene(self._h, C.byref(scene), C.byref(camera), C.byref(tables)))
         self.n = scene.num_wavelengths
+
+    def scene_upload_bytes(self):
+        v = C.c_size_t()
+        _check(lib().drt_cuda_scene_upload_bytes(self._h, C.byref(v)))
+        return v.value
 
     def set_geometry_precision(self, precision):
         _check(lib().drt_cuda_set_geometry_precision(self._h, precision))

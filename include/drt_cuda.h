@@ -69,6 +69,9 @@ void drt_cuda_destroy(drt_cuda_context *ctx);
 /* Copies scene, camera and tables to the device (f64 narrowed as the kernels need). */
 int  drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables);
 
+/* Bytes the last upload_scene copied host -> device. */
+int  drt_cuda_scene_upload_bytes(const drt_cuda_context *ctx, size_t *bytes);
+
 /* DRT_GEOMETRY_F32 (default) or DRT_GEOMETRY_F64; spectra and film are f32 in both. */
 int  drt_cuda_set_geometry_precision(drt_cuda_context *ctx, int precision);
 
