@@ -211,7 +211,7 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
         for(int k = 0; k < DRT_SPD_COUNT; k += 1)
         {
             if(!(scene->materials[m].spd_mask & (1 << k))) continue;
-            index.row[m][k] = rows++;
+            index.row[m][k] = (rows++) * index.npad;   /* word offset of the row in the pool */
             size_t at = pool.size();
             pool.resize(at + (size_t)index.npad, 0.f);
             for(int i = 0; i < n; i += 1) pool[at + (size_t)i] = (float)scene->materials[m].spd[k][i];

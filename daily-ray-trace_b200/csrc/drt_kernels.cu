@@ -252,9 +252,11 @@ template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g,
  * seven spectra: 1, diffuse, glossy, mirror, R_dielectric(on_dot), F_conductor(on_dot), F_conductor(mn_dot).  Walking
  * the lobe list with a 7-vector as the scratch reproduces the sum, stale values included, as 7 weights.  The weights
  * the material can produce (g.bmask) are stored to the record column `rec` (already offset to the slot) from word `at`. */
+#define BMASK_PLASTIC ((1 << BK_DIFFUSE) | (1 << BK_GLOSSY))
+
 template <typename R>
-__device__ __noinline__ void eval_weights(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in, int match, float scale,
-                                          float *rec, uint32_t at)
+__device__ __noinline__ void eval_weights_general(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in, int match, float scale,
+                                                  float *rec, uint32_t at)
 {
     const bool is_reflection = match & 1, is_transmission = match & 2;
     float cur[BK_COUNT], acc[BK_COUNT];
@@ -334,6 +336,25 @@ __device__ __noinline__ void eval_weights(const GeomT<R> &g, int m, V3<R> nrm, V
     if(mask & (1 << BK_COND_MN)) rec[at * DRT_WARP] = mn_cos;
 }
 
+/* Hot case inline: the two-lobe Blinn-Phong plastic (bp_diffuse_bdsf, bp_glossy_bdsf) of every shipped wall and ball
+ * needs two weights and no lobe walk; every other lobe list goes through the out-of-line general evaluator. */
+template <typename R>
+__device__ __forceinline__ void eval_weights(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in, int match, float scale,
+                                             float *rec, uint32_t at)
+{
+    if(g.bmask[m] == BMASK_PLASTIC && g.nlobes[m] == 2)
+    {
+        R cos_in = r_abs(dot(nrm, in));
+        V3<R> bis = normalise(out + in);
+        R nb = dot(nrm, bis);
+        R coef = r_pow((R(0) > nb) ? R(0) : nb, g.shin[m]);
+        rec[at * DRT_WARP] = (float)((R(1) / Num<R>::pi()) * cos_in) * scale;
+        rec[(at + 1) * DRT_WARP] = (float)(coef * cos_in) * scale;
+        return;
+    }
+    eval_weights_general<R>(g, m, nrm, out, on_dot, in, match, scale, rec, at);
+}
+
 /* dielectric Fresnel at one wavelength, bdsf.c:44-66 (Q9 kept) */
 template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr, T inc_cos)
 {
@@ -383,12 +404,17 @@ template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /
 }
 
 /* match: bit0 = `in` came out of the reflection formula, bit1 = out of the refraction formula (Q8) */
+template <typename R> struct DirSample { V3<R> in; R inv_pdf; int match; Rng rng; };
+
+/* All six samplers, out of line and by value (the cosine-weighted one is also inlined in sample_direction below). */
 template <typename R>
-__device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R> &h, Rng &rng, V3<R> &in, R &inv_pdf, int &match)
+__device__ __noinline__ DirSample<R> sample_direction_general(const GeomT<R> &g, Hit<R> h, Rng rng)
 {
+    DirSample<R> out;
+    V3<R> in = mk<R>(R(0), R(0), R(0));
+    R inv_pdf = R(0);
+    int match = 0;
     int m = h.surf_mat;
-    match = 0;
-    in = mk<R>(R(0), R(0), R(0)); inv_pdf = R(0);
     switch(g.dirf[m])
     {
         case DRT_DIR_UNIFORM_HEMISPHERE:   /* :191-198; uniform_sample_sphere rng.c:14-23 has z = u >= 0 */
@@ -476,6 +502,29 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
         }
         default: break;
     }
+    out.in = in; out.inv_pdf = inv_pdf; out.match = match; out.rng = rng;
+    return out;
+}
+
+template <typename R>
+__device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R> &h, Rng &rng, V3<R> &in, R &inv_pdf, int &match)
+{
+    if(g.dirf[h.surf_mat] == DRT_DIR_COS_WEIGHTED_HEMISPHERE)   /* hot case inline, bdsf.c:200-213 */
+    {
+        V3<R> q;
+        for(;;)
+        {
+            q = sample_disc<R>(rng);
+            if(dot(q, q) < R(1)) break;   /* Q16 */
+        }
+        q.z = r_sqrt(R(1) - dot(q, q));
+        in = rotate_from_z<R>(h.nrm, q);
+        inv_pdf = Num<R>::pi() / dot(h.nrm, in);
+        match = 0;
+        return;
+    }
+    DirSample<R> s = sample_direction_general<R>(g, h, rng);
+    in = s.in; inv_pdf = s.inv_pdf; match = s.match; rng = s.rng;
 }
 
 /* ------------------------------------------------------------------ path records in shared memory */
@@ -485,12 +534,17 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 #define REC_HEAD 2
 #define KIND_SHADE 1u
 #define KIND_EMIT  2u
+/* bounce header word:
+ *   fast (two-lobe plastic, one light):  kind(2) | 1<<2 | light visible<<3 | diffuse row offset(14)<<4 | glossy row offset(14)<<18
+ *   general:                             kind(2) | 0<<2 | surface material(5)<<3 | media swapped<<8 | light visibility mask(16)<<16
+ * so the hot replay needs ONE header read and no material-table lookups. */
+#define HDR_FAST 4u
 
 /* ------------------------------------------------------------------ phase 1: trace one path, emit its record
  * `rec` points at this lane's column (word w at rec[w*32]).  Returns the termination-histogram bin. */
 
 template <typename R>
-__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLaunch &L, float *rec,
+__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec,
                                                uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
 {
     Rng rng;
@@ -540,7 +594,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
         {
             if(flags & 2)
             {
-                rec[base * DRT_WARP] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 2));   /* Q6 */
+                rec[base * DRT_WARP] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
                 nb += 1;
             }
             end_depth = depth;
@@ -592,7 +646,11 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
         sample_direction<R>(g, h, rng, in, inv_pdf, match);
         eval_weights<R>(g, h.surf_mat, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, base + 2 + (ew + 1) * (uint32_t)g.nlights);
         uint32_t swapped = (h.inc_mat != g.base_mat) ? 1u : 0u;
-        rec[base * DRT_WARP] = __uint_as_float(KIND_SHADE | ((uint32_t)h.surf_mat << 2) | (swapped << 7) | (vis_mask << 8));
+        uint32_t hdr = KIND_SHADE | ((uint32_t)h.surf_mat << 3) | (swapped << 8) | (vis_mask << 16);
+        if(g.bmask[h.surf_mat] == BMASK_PLASTIC && g.nlobes[h.surf_mat] == 2 && g.nlights == 1)
+            hdr = KIND_SHADE | HDR_FAST | ((vis_mask & 1u) << 3) | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_DIFFUSE] << 4)
+                  | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_GLOSSY] << 18);
+        rec[base * DRT_WARP] = __uint_as_float(hdr);
         rec[(base + 1) * DRT_WARP] = (float)h.on_dot;
         nb += 1;
         d = in;
@@ -603,22 +661,19 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const RenderLa
     return (end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8;   /* histogram bin: depth of termination, 8 = hit the cap */
 }
 
-/* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp */
+/* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp
+ *
+ * Lane l holds wavelengths l, l+32, ... (NS register slots).  `col` is the record column of the path (word w at
+ * col[w*32]); every read of it is a shared-memory broadcast.  SpdIndex.row holds WORD OFFSETS into the pool. */
 
-/* One BSDF evaluation expanded over this lane's wavelengths.  `mask` (the material's basis set) is warp-uniform, so
- * every branch below is uniform; d_row/g_row are the material's diffuse/glossy rows already in registers. */
+template <int NS> struct Spec { float v[NS]; };
+template <int NS> struct ShadeState { Spec<NS> thr, dst; };
+
+/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform. */
 template <int NS>
-__device__ __forceinline__ void eval_spectrum(const float *col, uint32_t at, int mask, const float (&d_row)[NS], const float (&g_row)[NS],
-                                              const SpdIndex &ix, const float *pool_lane, int surf_mat, int inc_mat, int trans_mat, float on_dot,
-                                              bool &have_r, float (&rl)[NS], bool &have_f, float (&fl)[NS], float (&f)[NS])
+__device__ __forceinline__ void eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
+                                                      int surf_mat, int inc_mat, int trans_mat, float on_dot, float (&f)[NS])
 {
-    if(mask == ((1 << BK_DIFFUSE) | (1 << BK_GLOSSY)))   /* the Blinn-Phong plastic of every shipped wall */
-    {
-        float wd = col[at * DRT_WARP], wg = col[(at + 1) * DRT_WARP];
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(wg, g_row[k], wd * d_row[k]);
-        return;
-    }
     float base = 0.f;
     if(mask & (1 << BK_CONST)) { base = col[at * DRT_WARP]; at += 1; }
 #pragma unroll
@@ -626,37 +681,34 @@ __device__ __forceinline__ void eval_spectrum(const float *col, uint32_t at, int
     if(mask & (1 << BK_DIFFUSE))
     {
         float w = col[at * DRT_WARP]; at += 1;
+        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, d_row[k], f[k]);
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
     }
     if(mask & (1 << BK_GLOSSY))
     {
         float w = col[at * DRT_WARP]; at += 1;
+        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, g_row[k], f[k]);
+        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
     }
     if(mask & (1 << BK_MIRROR))
     {
         float w = col[at * DRT_WARP]; at += 1;
-        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR] * ix.npad;
+        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
 #pragma unroll
         for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
     }
+    const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT];
+    const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT];
+    const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT];
     if(mask & (1 << BK_DIEL_R))
     {
         float w = col[at * DRT_WARP]; at += 1;
         if(w != 0.f)
         {
-            if(!have_r)
-            {
-                const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
-                const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
 #pragma unroll
-                for(int k = 0; k < NS; k += 1) rl[k] = fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot);
-                have_r = true;
-            }
-#pragma unroll
-            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, rl[k], f[k]);
+            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot), f[k]);
         }
     }
     if(mask & (1 << BK_COND_ON))
@@ -664,17 +716,8 @@ __device__ __forceinline__ void eval_spectrum(const float *col, uint32_t at, int
         float w = col[at * DRT_WARP]; at += 1;
         if(w != 0.f)
         {
-            if(!have_f)
-            {
-                const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
-                const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
-                const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad;
 #pragma unroll
-                for(int k = 0; k < NS; k += 1) fl[k] = fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot);
-                have_f = true;
-            }
-#pragma unroll
-            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fl[k], f[k]);
+            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot), f[k]);
         }
     }
     if(mask & (1 << BK_COND_MN))
@@ -682,74 +725,97 @@ __device__ __forceinline__ void eval_spectrum(const float *col, uint32_t at, int
         float w = col[at * DRT_WARP], mn_cos = col[(at + 1) * DRT_WARP];
         if(w != 0.f)
         {
-            const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT] * ix.npad;
-            const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT] * ix.npad;
-            const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT] * ix.npad;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1)
-                f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], mn_cos), f[k]);
+            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], mn_cos), f[k]);
         }
     }
 }
 
+/* One shaded bounce of cast_ray (daily_ray_trace.c:458-473) for any material and any number of lights, out of line. */
+template <int NS, typename G>
+__device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, uint32_t base, uint32_t hdr, const G &g, const SpdIndex &ix,
+                                                            const float *pool_lane, uint32_t ew, int nlights, ShadeState<NS> st)
+{
+    const int surf_mat = (hdr >> 3) & 31;
+    const int mask = g.bmask[surf_mat];
+    const bool swapped = (hdr >> 8) & 1u;
+    const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
+    const uint32_t vis = hdr >> 16;
+    const float on_dot = col[(base + 1) * DRT_WARP];
+    float f[NS], contrib[NS];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) contrib[k] = 0.f;
+    for(int j = 0; j < nlights; j += 1)
+    {
+        if(!((vis >> j) & 1u)) continue;
+        uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+        eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, f);
+        float kk = col[(e + ew) * DRT_WARP];
+        const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
+    }
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], contrib[k], st.dst.v[k]);
+    eval_spectrum_general<NS>(col, base + 2 + (ew + 1) * (uint32_t)nlights, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, f);
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) st.thr.v[k] *= f[k];
+    return st;
+}
+
 /* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from record column `col` (nb >= 1 bounces);
- * returns the path contribution already multiplied by the vignette factor (:612-615). */
+ * returns the path contribution already multiplied by the vignette factor (:612-615).
+ * `e0` = emission of light 0 in registers (the only light of every shipped scene). */
 template <int NS, typename G>
 __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool_lane,
-                                            const RenderLaunch &L, float (&c)[NS])
+                                            const RenderLaunch &L, const float (&e0)[NS], float (&c)[NS])
 {
-    float thr[NS], dst[NS];
+    ShadeState<NS> st;
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) { thr[k] = 1.f; dst[k] = 0.f; }
+    for(int k = 0; k < NS; k += 1) { st.thr.v[k] = 1.f; st.dst.v[k] = 0.f; }
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
-    for(uint32_t b = 0; b < nb; b += 1)
+    const float *p = col + REC_HEAD * DRT_WARP;
+    uint32_t base = REC_HEAD;
+    uint32_t hdr_next = __float_as_uint(p[0]);
+    for(uint32_t b = 0; b < nb; b += 1, p += bw * DRT_WARP, base += bw)
     {
-        uint32_t base = REC_HEAD + b * bw;
-        uint32_t hdr = __float_as_uint(col[base * DRT_WARP]);
-        int surf_mat = (hdr >> 2) & 31;
-        if((hdr & 3u) == KIND_EMIT)
+        const uint32_t hdr = hdr_next;
+        if(b + 1 < nb) hdr_next = __float_as_uint(p[bw * DRT_WARP]);   /* next header in flight while this bounce is shaded */
+        if(hdr & HDR_FAST)
         {
-            const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_EMISSION] * ix.npad;
-#pragma unroll
-            for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], row[k * DRT_WARP], dst[k]);
-            break;
-        }
-        const int mask = g.bmask[surf_mat];
-        const bool swapped = (hdr >> 7) & 1u;
-        const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
-        const uint32_t vis = hdr >> 8;
-        const float on_dot = col[(base + 1) * DRT_WARP];
-        float d_row[NS], g_row[NS];
-        {
-            const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE] * ix.npad;
-            const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY] * ix.npad;
+            /* hot case: two-lobe plastic under one light.  Words: [2] wD [3] wG [2+ew] k (NEE), [3+ew] wD [4+ew] wG (sample) */
+            const float *dr = pool_lane + ((hdr >> 4) & 0x3fffu);
+            const float *gr = pool_lane + (hdr >> 18);
+            float d_row[NS], g_row[NS];
 #pragma unroll
             for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_WARP]; g_row[k] = gr[k * DRT_WARP]; }
-        }
-        bool have_r = false, have_f = false;
-        float rl[NS], fl[NS], f[NS], contrib[NS];
+            const float wd_n = p[2 * DRT_WARP], wg_n = p[3 * DRT_WARP], kk = p[(2 + ew) * DRT_WARP];
+            const float wd_s = p[(3 + ew) * DRT_WARP], wg_s = p[(4 + ew) * DRT_WARP];
+            if(hdr & 8u)   /* the light is visible */
+            {
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) { contrib[k] = 0.f; rl[k] = 0.f; fl[k] = 0.f; }
-        for(int j = 0; j < L.nlights; j += 1)
+                for(int k = 0; k < NS; k += 1)
+                {
+                    float f = fmaf(wg_n, g_row[k], wd_n * d_row[k]);
+                    st.dst.v[k] = fmaf(st.thr.v[k], (f * e0[k]) * kk, st.dst.v[k]);
+                }
+            }
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) st.thr.v[k] *= fmaf(wg_s, g_row[k], wd_s * d_row[k]);
+            continue;
+        }
+        if((hdr & 3u) == KIND_EMIT)
         {
-            if(!((vis >> j) & 1u)) continue;
-            uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
-            eval_spectrum<NS>(col, e, mask, d_row, g_row, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, have_r, rl, have_f, fl, f);
-            float kk = col[(e + ew) * DRT_WARP];
-            const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION] * ix.npad;
+            const float *row = pool_lane + ix.row[(hdr >> 3) & 31][DRT_SPD_EMISSION];
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
+            for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], row[k * DRT_WARP], st.dst.v[k]);
+            break;
         }
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) dst[k] = fmaf(thr[k], contrib[k], dst[k]);
-        eval_spectrum<NS>(col, base + 2 + (ew + 1) * (uint32_t)L.nlights, mask, d_row, g_row, ix, pool_lane, surf_mat, inc_mat, trans_mat,
-                          on_dot, have_r, rl, have_f, fl, f);
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) thr[k] *= f[k];
+        st = shade_bounce_general<NS, G>(col, base, hdr, g, ix, pool_lane, ew, L.nlights, st);
     }
-    float vig = col[REC_VIG * DRT_WARP];
+    const float vig = col[REC_VIG * DRT_WARP];
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) c[k] = dst[k] * vig;
+    for(int k = 0; k < NS; k += 1) c[k] = st.dst.v[k] * vig;
 }
 
 /* film of one pixel held by a warp: lane l owns wavelengths l, l+32, ... */
@@ -763,36 +829,11 @@ template <int NS> struct PixelFilm
 #pragma unroll
         for(int k = 0; k < NS; k += 1) { sum[k] = 0.f; mean[k] = 0.f; m2[k] = 0.f; }
     }
-    __device__ __forceinline__ void load(const FilmPtrs &film, uint32_t gpix, uint32_t n, uint32_t lane)
-    {
-        cnt = film.filter[gpix]; lit = true;
-#pragma unroll
-        for(int k = 0; k < NS; k += 1)
-        {
-            uint32_t wl = lane + k * DRT_WARP;
-            size_t at = (size_t)gpix * n + wl;
-            sum[k] = (wl < n) ? film.sum[at] : 0.f; mean[k] = (wl < n) ? film.mean[at] : 0.f; m2[k] = (wl < n) ? film.m2[at] : 0.f;
-        }
-    }
-    __device__ __forceinline__ void store(const FilmPtrs &film, uint32_t gpix, uint32_t n, uint32_t lane) const
-    {
-#pragma unroll
-        for(int k = 0; k < NS; k += 1)
-        {
-            uint32_t wl = lane + k * DRT_WARP;
-            if(wl < n)
-            {
-                size_t at = (size_t)gpix * n + wl;
-                film.sum[at] = sum[k]; film.mean[at] = mean[k]; film.m2[at] = m2[k];
-            }
-        }
-        if(lane == 0) film.filter[gpix] = cnt;
-    }
     /* K6: film accumulation + Welford, daily_ray_trace.c:732-743 (filter weight is the constant 1, Q20) */
     __device__ __forceinline__ void add(const float (&c)[NS])
     {
         cnt += 1.f; lit = true;
-        float inv = 1.f / cnt;
+        float inv = __frcp_rn(cnt);
 #pragma unroll
         for(int k = 0; k < NS; k += 1)
         {
@@ -807,7 +848,7 @@ template <int NS> struct PixelFilm
     {
         cnt += 1.f;
         if(!lit) return;
-        float inv = 1.f / cnt;
+        float inv = __frcp_rn(cnt);
 #pragma unroll
         for(int k = 0; k < NS; k += 1)
         {
@@ -817,6 +858,38 @@ template <int NS> struct PixelFilm
         }
     }
 };
+
+/* film <-> HBM, once per pixel per render: out of line (cold relative to the per-sample code) and by value */
+template <int NS>
+__device__ __noinline__ PixelFilm<NS> film_load(FilmPtrs film, uint32_t gpix, uint32_t n, uint32_t lane)
+{
+    PixelFilm<NS> f;
+    f.cnt = film.filter[gpix]; f.lit = true;
+#pragma unroll
+    for(int k = 0; k < NS; k += 1)
+    {
+        uint32_t wl = lane + k * DRT_WARP;
+        size_t at = (size_t)gpix * n + wl;
+        f.sum[k] = (wl < n) ? film.sum[at] : 0.f; f.mean[k] = (wl < n) ? film.mean[at] : 0.f; f.m2[k] = (wl < n) ? film.m2[at] : 0.f;
+    }
+    return f;
+}
+
+template <int NS>
+__device__ __noinline__ void film_store(FilmPtrs film, uint32_t gpix, uint32_t n, uint32_t lane, PixelFilm<NS> f)
+{
+#pragma unroll
+    for(int k = 0; k < NS; k += 1)
+    {
+        uint32_t wl = lane + k * DRT_WARP;
+        if(wl < n)
+        {
+            size_t at = (size_t)gpix * n + wl;
+            film.sum[at] = f.sum[k]; film.mean[at] = f.mean[k]; film.m2[at] = f.m2[k];
+        }
+    }
+    if(lane == 0) film.filter[gpix] = f.cnt;
+}
 
 /* ------------------------------------------------------------------ the kernel */
 
@@ -858,6 +931,10 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
     const uint32_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
     const bool have_film = L.film.sum != nullptr;
 
+    float e0[NS];   /* emission of light 0, kept in registers for the whole kernel */
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) e0[k] = (L.nlights > 0) ? pool_lane[ix.row[g.mat[g.light_surf[0]]][DRT_SPD_EMISSION] + k * DRT_WARP] : 0.f;
+
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
     uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
     for(;;)
@@ -875,7 +952,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
         uint32_t cur_lp = p_begin, cur_x = L.x0 + p_begin % rw, cur_y = L.y0 + p_begin / rw, cur_s = 0;
         PixelFilm<NS> film;
         film.clear();
-        if(L.accumulate && have_film) film.load(L.film, cur_y * L.width + cur_x, n, lane);
+        if(L.accumulate && have_film) film = film_load<NS>(L.film, cur_y * L.width + cur_x, n, lane);
 
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
@@ -886,7 +963,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
             {
                 uint32_t lp = p_begin, s = q;
                 if(L.pixels_per_task > 1) { lp += q / spp; s = q % spp; }
-                bin = trace_path<R>(g, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
+                bin = trace_path<R>(g, ix, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
             }
             __syncwarp();
 #pragma unroll
@@ -902,12 +979,12 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
             {
                 if(cur_s == spp)   /* next pixel of the task (only when a task holds several pixels, spp < 32) */
                 {
-                    if(have_film) film.store(L.film, cur_y * L.width + cur_x, n, lane);
+                    if(have_film) film_store<NS>(L.film, cur_y * L.width + cur_x, n, lane, film);
                     cur_lp += 1; cur_s = 0;
                     cur_x += 1;
                     if(cur_x == L.x1) { cur_x = L.x0; cur_y += 1; }
                     film.clear();
-                    if(L.accumulate && have_film) film.load(L.film, cur_y * L.width + cur_x, n, lane);
+                    if(L.accumulate && have_film) film = film_load<NS>(L.film, cur_y * L.width + cur_x, n, lane);
                 }
                 const uint32_t nb = __shfl_sync(0xffffffffu, my_nb, slot);
                 float c[NS];
@@ -919,7 +996,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
                 }
                 else
                 {
-                    replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, c);
+                    replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, e0, c);
                     film.add(c);
                 }
                 if(L.path_dump)
@@ -935,7 +1012,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const Render
             }
             __syncwarp();
         }
-        if(have_film) film.store(L.film, cur_y * L.width + cur_x, n, lane);
+        if(have_film) film_store<NS>(L.film, cur_y * L.width + cur_x, n, lane, film);
     }
 
     /* work counters: one shared-memory atomic per warp per counter, then one global atomic per CTA per counter */
