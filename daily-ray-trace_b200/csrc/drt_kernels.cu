@@ -669,35 +669,28 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
 template <int NS> struct Spec { float v[NS]; };
 template <int NS> struct ShadeState { Spec<NS> thr, dst; };
 
-/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform. */
+/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform.  Out of line and
+ * written so that each Fresnel formula is instantiated once: this code is cold for the shipped walls but must stay small
+ * enough not to evict the hot path from the instruction cache when a scene does use mirrors, glass or metals. */
 template <int NS>
-__device__ __forceinline__ void eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
-                                                      int surf_mat, int inc_mat, int trans_mat, float on_dot, float (&f)[NS])
+__device__ __noinline__ Spec<NS> eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
+                                                       int surf_mat, int inc_mat, int trans_mat, float on_dot)
 {
+    Spec<NS> f;
     float base = 0.f;
     if(mask & (1 << BK_CONST)) { base = col[at * DRT_WARP]; at += 1; }
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) f[k] = base;
-    if(mask & (1 << BK_DIFFUSE))
+    for(int k = 0; k < NS; k += 1) f.v[k] = base;
+    /* the three table lobes share one multiply-add loop: (weight, row) pairs in mask order */
+#pragma unroll 1
+    for(int kind = BK_DIFFUSE; kind <= BK_MIRROR; kind += 1)
     {
+        if(!(mask & (1 << kind))) continue;
         float w = col[at * DRT_WARP]; at += 1;
-        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];
+        int spd = (kind == BK_DIFFUSE) ? DRT_SPD_DIFFUSE : (kind == BK_GLOSSY) ? DRT_SPD_GLOSSY : DRT_SPD_MIRROR;
+        const float *row = pool_lane + ix.row[surf_mat][spd];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
-    }
-    if(mask & (1 << BK_GLOSSY))
-    {
-        float w = col[at * DRT_WARP]; at += 1;
-        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
-    }
-    if(mask & (1 << BK_MIRROR))
-    {
-        float w = col[at * DRT_WARP]; at += 1;
-        const float *row = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, row[k * DRT_WARP], f[k]);
+        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, row[k * DRT_WARP], f.v[k]);
     }
     const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT];
     const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT];
@@ -708,27 +701,22 @@ __device__ __forceinline__ void eval_spectrum_general(const float *col, uint32_t
         if(w != 0.f)
         {
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot), f[k]);
+            for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot), f.v[k]);
         }
     }
-    if(mask & (1 << BK_COND_ON))
+    /* conductor terms: F(on_dot) of fs_conductor_bdsf and/or F(mn_dot) of ct_conductor_bdsf, one loop body for both */
+    float w_a = 0.f, c_a = 0.f, w_b = 0.f, c_b = 0.f;
+    if(mask & (1 << BK_COND_ON)) { w_a = col[at * DRT_WARP]; c_a = on_dot; at += 1; }
+    if(mask & (1 << BK_COND_MN)) { w_b = col[at * DRT_WARP]; c_b = col[(at + 1) * DRT_WARP]; }
+#pragma unroll 1
+    for(int t = 0; t < 2; t += 1)
     {
-        float w = col[at * DRT_WARP]; at += 1;
-        if(w != 0.f)
-        {
+        float w = t ? w_b : w_a, cs = t ? c_b : c_a;
+        if(w == 0.f) continue;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], on_dot), f[k]);
-        }
+        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], cs), f.v[k]);
     }
-    if(mask & (1 << BK_COND_MN))
-    {
-        float w = col[at * DRT_WARP], mn_cos = col[(at + 1) * DRT_WARP];
-        if(w != 0.f)
-        {
-#pragma unroll
-            for(int k = 0; k < NS; k += 1) f[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], mn_cos), f[k]);
-        }
-    }
+    return f;
 }
 
 /* One shaded bounce of cast_ray (daily_ray_trace.c:458-473) for any material and any number of lights, out of line. */
@@ -742,24 +730,25 @@ __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, ui
     const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
     const uint32_t vis = hdr >> 16;
     const float on_dot = col[(base + 1) * DRT_WARP];
-    float f[NS], contrib[NS];
+    float contrib[NS];
 #pragma unroll
     for(int k = 0; k < NS; k += 1) contrib[k] = 0.f;
+#pragma unroll 1
     for(int j = 0; j < nlights; j += 1)
     {
         if(!((vis >> j) & 1u)) continue;
         uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
-        eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, f);
+        Spec<NS> f = eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot);
         float kk = col[(e + ew) * DRT_WARP];
         const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
+        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
     }
 #pragma unroll
     for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], contrib[k], st.dst.v[k]);
-    eval_spectrum_general<NS>(col, base + 2 + (ew + 1) * (uint32_t)nlights, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot, f);
+    Spec<NS> f = eval_spectrum_general<NS>(col, base + 2 + (ew + 1) * (uint32_t)nlights, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot);
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) st.thr.v[k] *= f[k];
+    for(int k = 0; k < NS; k += 1) st.thr.v[k] *= f.v[k];
     return st;
 }
 
