@@ -296,7 +296,10 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
         return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
                     p->max_depth, ctx->nlights, smem, ctx->smem_optin);
     int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    int by_threads = 16 / warps;    /* 128 registers per thread: at most 16 resident warps per SM */
+#ifndef DRT_MIN_CTAS
+#define DRT_MIN_CTAS 2
+#endif
+    int by_threads = (DRT_MIN_CTAS * DRT_CTA_WARPS) / warps;    /* register budget of __launch_bounds__(256, DRT_MIN_CTAS) */
     if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if(ctas_per_sm < 1) ctas_per_sm = 1;
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);

@@ -529,6 +529,9 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 
 /* ------------------------------------------------------------------ path records in shared memory */
 
+#ifndef DRT_MIN_CTAS
+#define DRT_MIN_CTAS 2
+#endif
 #define REC_NB   0
 #define REC_VIG  1
 #define REC_HEAD 2
@@ -661,6 +664,57 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     return (end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8;   /* histogram bin: depth of termination, 8 = hit the cap */
 }
 
+/* ------------------------------------------------------------------ packed f32x2 arithmetic (sm_100 fma.rn.f32x2)
+ * The replay is bound by instruction issue, not by the FMA pipe: one packed instruction does the work of two for the
+ * wavelength slots (0,1), (2,3); an odd last slot stays scalar.  Results are bit-identical to the scalar forms. */
+__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{ unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{ unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
+{ unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+/* o = a*b + c,  o = s*b + c,  o = a*b,  o = s*b  over NS wavelength slots */
+template <int NS> __device__ __forceinline__ void v_fma(float (&o)[NS], const float (&a)[NS], const float (&b)[NS], const float (&c)[NS])
+{
+#pragma unroll
+    for(int k = 0; k + 1 < NS; k += 2) upk2(fma2(pk2(a[k], a[k + 1]), pk2(b[k], b[k + 1]), pk2(c[k], c[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = fmaf(a[NS - 1], b[NS - 1], c[NS - 1]);
+}
+template <int NS> __device__ __forceinline__ void v_fma_s(float (&o)[NS], float s, const float (&b)[NS], const float (&c)[NS])
+{
+#pragma unroll
+    for(int k = 0; k + 1 < NS; k += 2) upk2(fma2(pk2(s, s), pk2(b[k], b[k + 1]), pk2(c[k], c[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = fmaf(s, b[NS - 1], c[NS - 1]);
+}
+template <int NS> __device__ __forceinline__ void v_mul(float (&o)[NS], const float (&a)[NS], const float (&b)[NS])
+{
+#pragma unroll
+    for(int k = 0; k + 1 < NS; k += 2) upk2(mul2(pk2(a[k], a[k + 1]), pk2(b[k], b[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = a[NS - 1] * b[NS - 1];
+}
+template <int NS> __device__ __forceinline__ void v_mul_s(float (&o)[NS], float s, const float (&b)[NS])
+{
+#pragma unroll
+    for(int k = 0; k + 1 < NS; k += 2) upk2(mul2(pk2(s, s), pk2(b[k], b[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = s * b[NS - 1];
+}
+template <int NS> __device__ __forceinline__ void v_add(float (&o)[NS], const float (&a)[NS], const float (&b)[NS])
+{
+#pragma unroll
+    for(int k = 0; k + 1 < NS; k += 2) upk2(add2(pk2(a[k], a[k + 1]), pk2(b[k], b[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = a[NS - 1] + b[NS - 1];
+}
+template <int NS> __device__ __forceinline__ void v_sub(float (&o)[NS], const float (&a)[NS], const float (&b)[NS])
+{
+    float nb[NS];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) nb[k] = -b[k];
+    v_add<NS>(o, a, nb);
+}
+
 /* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp
  *
  * Lane l holds wavelengths l, l+32, ... (NS register slots).  `col` is the record column of the path (word w at
@@ -780,17 +834,18 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
             for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_WARP]; g_row[k] = gr[k * DRT_WARP]; }
             const float wd_n = p[2 * DRT_WARP], wg_n = p[3 * DRT_WARP], kk = p[(2 + ew) * DRT_WARP];
             const float wd_s = p[(3 + ew) * DRT_WARP], wg_s = p[(4 + ew) * DRT_WARP];
+            float f[NS], t[NS];
             if(hdr & 8u)   /* the light is visible */
             {
-#pragma unroll
-                for(int k = 0; k < NS; k += 1)
-                {
-                    float f = fmaf(wg_n, g_row[k], wd_n * d_row[k]);
-                    st.dst.v[k] = fmaf(st.thr.v[k], (f * e0[k]) * kk, st.dst.v[k]);
-                }
+                v_mul_s<NS>(t, wd_n, d_row);
+                v_fma_s<NS>(f, wg_n, g_row, t);          /* f = wd*D + wg*G */
+                v_mul<NS>(f, f, e0);
+                v_mul_s<NS>(f, kk, f);                   /* (f * E) * k */
+                v_fma<NS>(st.dst.v, st.thr.v, f, st.dst.v);
             }
-#pragma unroll
-            for(int k = 0; k < NS; k += 1) st.thr.v[k] *= fmaf(wg_s, g_row[k], wd_s * d_row[k]);
+            v_mul_s<NS>(t, wd_s, d_row);
+            v_fma_s<NS>(f, wg_s, g_row, t);
+            v_mul<NS>(st.thr.v, st.thr.v, f);
             continue;
         }
         if((hdr & 3u) == KIND_EMIT)
@@ -823,14 +878,12 @@ template <int NS> struct PixelFilm
     {
         cnt += 1.f; lit = true;
         float inv = __frcp_rn(cnt);
-#pragma unroll
-        for(int k = 0; k < NS; k += 1)
-        {
-            sum[k] += c[k];
-            float delta = c[k] - mean[k];
-            mean[k] = fmaf(delta, inv, mean[k]);
-            m2[k] = fmaf(delta, c[k] - mean[k], m2[k]);
-        }
+        float delta[NS], rest[NS];
+        v_add<NS>(sum, sum, c);
+        v_sub<NS>(delta, c, mean);
+        v_fma_s<NS>(mean, inv, delta, mean);
+        v_sub<NS>(rest, c, mean);
+        v_fma<NS>(m2, delta, rest, m2);
     }
     /* the same update for a path that contributed nothing: exact no-op on an all-zero pixel */
     __device__ __forceinline__ void add_zero()
@@ -883,7 +936,7 @@ __device__ __noinline__ void film_store(FilmPtrs film, uint32_t gpix, uint32_t n
 /* ------------------------------------------------------------------ the kernel */
 
 template <typename R, int NS>
-__global__ void __launch_bounds__(DRT_CTA_THREADS, 2) render_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
