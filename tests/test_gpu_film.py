@@ -1,0 +1,136 @@
+"""GPU tier: film epilogues (K7 SPD->XYZ->RGB->u8, Chan merge), ragged shapes, the 4096^2 configuration, accumulate mode."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import common
+import oracledriver
+
+cuda = importlib.import_module("daily-ray-trace_b200.cuda")
+film_mod = importlib.import_module("daily-ray-trace_b200.film")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cuda.Context(0)
+    yield c
+    c.close()
+
+
+def _rel(a, b, floor_frac=1e-5):
+    floor = floor_frac * max(float(np.abs(b).max()), 1e-30)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+@pytest.mark.parametrize("w,h,spp", [(1, 1, 1), (7, 3, 5), (33, 17, 31), (16, 16, 32), (9, 5, 67), (13, 11, 100)])
+def test_ragged_shapes_match_oracle(ctx, w, h, spp):
+    """Image sizes and sample counts that are not multiples of the warp batch (32): pixels per task, partial batches."""
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, spp, 4)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    prm = oracledriver.params(w, h, 0, spp, 4, cfg.pixel_scheme, 1234)
+    film = ctx.render_host(prm)
+    gpu_paths = ctx.sample_paths(prm, 0, 0, w, h)
+    o_sum, o_avg, o_m2, o_paths, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h, want_paths=True)
+    n = scene.num_wavelengths
+    assert ctx.stats().paths == w * h * spp
+    assert np.array_equal(film["filter"], np.full(w * h, spp, np.float32))
+    assert (common.path_errors(gpu_paths, o_paths) <= 1e-4).mean() >= 0.995
+    for name, ref in (("sum", o_sum[:, :n]), ("mean", o_avg), ("m2", o_m2)):
+        assert (_rel(film[name], ref).max(axis=1) <= 2e-3).mean() >= 0.99, name
+
+
+def test_film_to_rgb_matches_host_conversion(ctx, host):
+    import torch
+    w, h, spp = 40, 24, 16
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, spp, 4)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    film = film_mod.FilmPlanes(w, h, n, torch.device("cuda", 0))
+    prm = oracledriver.params(w, h, 0, spp, 4, cfg.pixel_scheme, 5)
+    ctx.render_device(prm, film.as_drt_film())
+    rgb = torch.zeros(w * h, 3, device="cuda")
+    bgra = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+    L = host.lib()
+    dp = C.POINTER(C.c_double)
+    planes = {0: (film.sum / film.filter.unsqueeze(1)), 1: film.mean, 2: film.m2 / film.m2.max(dim=1, keepdim=True).values}
+    for which in (0, 1, 2):
+        ctx.film_to_rgb(film.as_drt_film(), w, h, which, rgb.data_ptr(), bgra.data_ptr())
+        torch.cuda.synchronize()
+        src = planes[which].double().cpu().numpy()
+        got_rgb, got_q = rgb.cpu().numpy(), bgra.cpu().numpy().view(np.uint32)
+        worst = 0
+        for p in range(0, w * h, 7):
+            spd = np.ascontiguousarray(src[p])
+            ref = np.zeros(3)
+            L.drt_spectrum_to_rgb(C.byref(tables), spd.ctypes.data_as(dp), ref.ctypes.data_as(dp))
+            if np.isnan(ref).any():
+                assert got_q[p] == 0          # 0/0 variance pixel -> NaN -> byte 0 (Q17)
+                continue
+            assert np.allclose(got_rgb[p], ref, rtol=2e-4, atol=2e-6), (which, p)
+            q = L.drt_rgb_to_bgra8(ref.ctypes.data_as(dp))
+            diff = max(abs(int((got_q[p] >> s) & 255) - int((q >> s) & 255)) for s in (0, 8, 16))
+            worst = max(worst, diff)
+        assert worst <= 1            # truncating quantiser: f32 vs f64 may differ by one code at a boundary
+
+
+def test_film_merge_kernel_matches_single_render(ctx):
+    """Two sample ranges rendered separately and merged on the device (the pairwise step of multi-GPU sharding)."""
+    import torch
+    w, h, depth = 32, 24, 4
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, 64, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    dev = torch.device("cuda", 0)
+    whole, a, b = (film_mod.FilmPlanes(w, h, n, dev) for _ in range(3))
+    ctx.render_device(oracledriver.params(w, h, 0, 64, depth, cfg.pixel_scheme, 3), whole.as_drt_film())
+    ctx.render_device(oracledriver.params(w, h, 0, 24, depth, cfg.pixel_scheme, 3), a.as_drt_film())
+    ctx.render_device(oracledriver.params(w, h, 24, 64, depth, cfg.pixel_scheme, 3), b.as_drt_film())
+    torch.cuda.synchronize()
+    a2 = film_mod.FilmPlanes(w, h, n, dev)
+    for name in ("sum", "filter", "mean", "m2"):
+        getattr(a2, name).copy_(getattr(a, name))
+    ctx.film_merge(a.as_drt_film(), b.as_drt_film(), w, h)          # CUDA kernel
+    film_mod.merge_pair_(a2, b)                                      # the same arithmetic in torch
+    torch.cuda.synchronize()
+    assert torch.equal(a.filter, whole.filter)
+    for name in ("sum", "mean", "m2"):
+        got, ref, tw = getattr(a, name).cpu().numpy(), getattr(whole, name).cpu().numpy(), getattr(a2, name).cpu().numpy()
+        assert _rel(got, ref).max() < 2e-4, name
+        assert _rel(got, tw).max() < 2e-5, name
+
+
+def test_4096_square_large_box_tiles(ctx):
+    """BASELINE configs[4] geometry: cornell_large_box at 4096x4096 (13.9 GB of film, > 4 GiB offsets), checked on tiles
+    against the oracle as the reference itself cannot allocate this frame (u32 sizes, Q22)."""
+    import torch
+    w = h = 4096
+    spp, depth = 2, 4
+    free, _ = torch.cuda.mem_get_info()
+    if free < 16 * 2 ** 30:
+        pytest.skip("needs 16 GB of free device memory")
+    cfg, tables, scene, camera = common.load("cornell_large_box", w, h, spp, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    n = scene.num_wavelengths
+    film = film_mod.FilmPlanes(w, h, n, torch.device("cuda", 0))
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 77)
+    ctx.render_device(prm, film.as_drt_film())
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    assert st.paths == w * h * spp
+    assert float(film.filter.min()) == spp == float(film.filter.max())
+    for (x0, y0) in ((0, 0), (2040, 2040), (4080, 4080), (4088, 8)):
+        x1, y1 = x0 + 8, y0 + 8
+        o_sum, o_avg, o_m2, _, _ = oracledriver.render_tile(scene, camera, prm, x0, y0, x1, y1)
+        rows = torch.arange(y0, y1).unsqueeze(1) * w + torch.arange(x0, x1).unsqueeze(0)
+        got = film.sum[rows.flatten().cuda()].cpu().numpy()
+        assert (_rel(got, o_sum[:, :n]).max(axis=1) <= 1e-3).mean() >= 0.98, (x0, y0)
+    del film
+    torch.cuda.empty_cache()
