@@ -21,6 +21,8 @@ void        drt_launch_film_to_rgb(const void *tables, const float *plane, const
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
 void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
 void        drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream_t stream);
+void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end,
+                                         uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream);
 size_t      drt_rgb_tables_bytes(void);
 void        drt_fill_rgb_tables(void *dst_host, const drt_tables *t);
 
@@ -268,7 +270,7 @@ extern "C" int drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, 
 }
 
 static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
-                  FilmPtrs film, float *dump, int accumulate, cudaStream_t stream)
+                  FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr)
 {
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
@@ -279,7 +281,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     memset(&L, 0, sizeof(L));
     L.geom = ctx->f64_geometry ? ctx->d_geom64 : ctx->d_geom32;
     L.spd_index = ctx->d_index; L.pool = ctx->d_pool; L.pool_words = ctx->pool_words;
-    L.film = film; L.path_dump = dump; L.stats = ctx->d_stats; L.task_counter = ctx->d_counter;
+    L.film = film; L.path_dump = dump; L.record_dump = record_dump; L.stats = ctx->d_stats; L.task_counter = ctx->d_counter;
     L.width = p->width; L.height = p->height; L.x0 = x0; L.y0 = y0; L.x1 = x1; L.y1 = y1;
     L.sample_begin = p->sample_begin; L.sample_end = p->sample_end; L.max_depth = p->max_depth;
     L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
@@ -288,6 +290,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.eval_words = (uint32_t)ctx->eval_words;
     L.bounce_words = 2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words;
     L.path_words = 2 + p->max_depth * L.bounce_words;
+    if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
     int warps = DRT_CTA_WARPS;
     size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps);
@@ -385,6 +388,26 @@ extern "C" int drt_cuda_sample_paths(drt_cuda_context *ctx, const drt_render_par
     return DRT_CUDA_OK;
 }
 
+extern "C" int drt_cuda_debug_records(drt_cuda_context *ctx, const drt_render_params *params, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                                      float *out_host, size_t out_capacity_words, uint32_t *words_per_path)
+{
+    if(!ctx || !params || !words_per_path) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    if(x1 <= x0 || y1 <= y0 || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "empty rectangle or sample range");
+    CU(cudaSetDevice(ctx->device));
+    FilmPtrs none = { nullptr, nullptr, nullptr, nullptr };
+    int rc = launch(ctx, params, x0, y0, x1, y1, none, nullptr, 0, 0, nullptr, words_per_path);   /* size query only */
+    if(rc != DRT_CUDA_OK || !out_host) return rc;
+    size_t words = (size_t)(x1 - x0) * (y1 - y0) * (params->sample_end - params->sample_begin) * (size_t)*words_per_path;
+    if(words > out_capacity_words) return fail(DRT_CUDA_E_ARG, "record buffer too small: need %zu words", words);
+    rc = ensure(&ctx->d_dump, &ctx->dump_bytes, words * 4);
+    if(rc != DRT_CUDA_OK) return rc;
+    rc = launch(ctx, params, x0, y0, x1, y1, none, nullptr, 0, 0, ctx->d_dump, nullptr);
+    if(rc != DRT_CUDA_OK) return rc;
+    CU(cudaMemcpy(out_host, ctx->d_dump, words * 4, cudaMemcpyDeviceToHost));
+    return DRT_CUDA_OK;
+}
+
 extern "C" int drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film, uint32_t width, uint32_t height, int which,
                                     float *rgb_device, uint32_t *bgra_device, void *stream)
 {
@@ -411,6 +434,88 @@ extern "C" int drt_cuda_film_merge(drt_cuda_context *ctx, const drt_film *dst, c
     drt_launch_film_merge(d, s, (uint32_t)ctx->n, (size_t)width * height, ctx->num_sms * 8, (cudaStream_t)stream);
     CU(cudaGetLastError());
     ctx->launches += 2;
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_alloc(drt_cuda_context *ctx, uint32_t width, uint32_t height, drt_film *out)
+{
+    if(!ctx || !out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    CU(cudaSetDevice(ctx->device));
+    size_t npix = (size_t)width * height, plane = npix * (size_t)ctx->n * 4;
+    memset(out, 0, sizeof(*out));
+    CU(cudaMalloc(&out->sum, plane)); CU(cudaMalloc(&out->mean, plane)); CU(cudaMalloc(&out->m2, plane)); CU(cudaMalloc(&out->filter, npix * 4));
+    CU(cudaMemset(out->sum, 0, plane)); CU(cudaMemset(out->mean, 0, plane)); CU(cudaMemset(out->m2, 0, plane)); CU(cudaMemset(out->filter, 0, npix * 4));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_free(drt_cuda_context *ctx, drt_film *film)
+{
+    if(!ctx || !film) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaFree(film->sum); cudaFree(film->mean); cudaFree(film->m2); cudaFree(film->filter);
+    memset(film, 0, sizeof(*film));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_ipc_export(drt_cuda_context *ctx, const drt_film *film, unsigned char handles[4][64])
+{
+    if(!ctx || !film || !handles) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    float *ptrs[4] = { film->sum, film->filter, film->mean, film->m2 };
+    for(int i = 0; i < 4; i += 1)
+    {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(handles[i], &h, 64);
+    }
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_ipc_open(drt_cuda_context *ctx, const unsigned char handles[4][64], drt_film *out)
+{
+    if(!ctx || !handles || !out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    void *ptrs[4] = { nullptr, nullptr, nullptr, nullptr };
+    for(int i = 0; i < 4; i += 1)
+    {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[i], 64);
+        CU(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    out->sum = (float *)ptrs[0]; out->filter = (float *)ptrs[1]; out->mean = (float *)ptrs[2]; out->m2 = (float *)ptrs[3];
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_ipc_close(drt_cuda_context *ctx, drt_film *mapped)
+{
+    if(!ctx || !mapped) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcCloseMemHandle(mapped->sum); cudaIpcCloseMemHandle(mapped->filter); cudaIpcCloseMemHandle(mapped->mean); cudaIpcCloseMemHandle(mapped->m2);
+    memset(mapped, 0, sizeof(*mapped));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *dst, const drt_film *srcs, int count, uint32_t width, uint32_t height,
+                                        uint64_t pixel_begin, uint64_t pixel_end, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream)
+{
+    if(!ctx || !dst || !srcs || count < 1 || count > 16) return fail(DRT_CUDA_E_ARG, "bad argument (1..16 films)");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    uint64_t npix = (uint64_t)width * height;
+    if(pixel_begin > pixel_end || pixel_end > npix) return fail(DRT_CUDA_E_ARG, "bad pixel range");
+    if((bgra_sum || bgra_mean || bgra_var) && !(bgra_sum && bgra_mean && bgra_var)) return fail(DRT_CUDA_E_ARG, "give all three image buffers or none");
+    CU(cudaSetDevice(ctx->device));
+    FilmPtrs films[16];
+    for(int i = 0; i < count; i += 1) films[i] = FilmPtrs{ srcs[i].sum, srcs[i].filter, srcs[i].mean, srcs[i].m2 };
+    FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 };
+    if(pixel_end > pixel_begin)
+    {
+        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, bgra_sum, bgra_mean, bgra_var,
+                                     ctx->num_sms * 8, (cudaStream_t)stream);
+        CU(cudaGetLastError());
+        ctx->launches += 1;
+    }
     return DRT_CUDA_OK;
 }
 

@@ -78,6 +78,7 @@ struct RenderLaunch
     const float    *pool;
     FilmPtrs        film;
     float          *path_dump;     /* optional per-path spectra, [pixel_local][sample][N] */
+    float          *record_dump;   /* optional per-path record words, [pixel_local][sample][path_words] (diagnostics) */
     DeviceStats    *stats;
     unsigned int   *task_counter;
     uint32_t width, height;

@@ -121,6 +121,101 @@ __global__ void __launch_bounds__(256) film_merge_filter_kernel(float *dst, cons
     for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) dst[i] = dst[i] + src[i];
 }
 
+
+/* Fused multi-GPU epilogue.  `set` holds the partial films of all ranks (own memory and peer memory mapped through
+ * CUDA IPC / P2P); every warp takes pixels of [pixel_begin, pixel_end), reads each rank's (count, sum, mean, M2) row
+ * straight over NVLink, combines them with Chan's update in registers, writes the merged planes to `dst` (which may
+ * itself be the root rank's memory) and, in the same pass, converts the three images of win32_main.c:150-152
+ * (sum/filter, mean, M2/max) to packed BGRA.  One kernel replaces reduce-scatter + gather + three conversions. */
+struct FilmSet { int count; FilmPtrs film[16]; };
+
+__global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables *tables, FilmSet set, FilmPtrs dst, uint32_t pixel_begin,
+                                                                uint32_t pixel_end, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
+{
+    __shared__ RgbTables t;
+    for(uint32_t i = threadIdx.x; i < sizeof(RgbTables) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(&t)[i] = reinterpret_cast<const uint32_t *>(tables)[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n = (uint32_t)t.n;
+    for(uint32_t p = pixel_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); p < pixel_end; p += warps)
+    {
+        float cnt = 0.f, sum[DRT_MAX_SLOTS], mean[DRT_MAX_SLOTS], m2[DRT_MAX_SLOTS];
+#pragma unroll
+        for(int k = 0; k < DRT_MAX_SLOTS; k += 1) { sum[k] = 0.f; mean[k] = 0.f; m2[k] = 0.f; }
+        for(int g = 0; g < set.count; g += 1)
+        {
+            const FilmPtrs &f = set.film[g];
+            float nb = f.filter[p];
+            float nab = cnt + nb;
+            float wb = (nab > 0.f) ? nb / nab : 0.f;
+#pragma unroll
+            for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+            {
+                uint32_t wl = lane + k * 32;
+                if(wl >= n) continue;
+                size_t at = (size_t)p * n + wl;
+                float mb = f.mean[at], delta = mb - mean[k];
+                m2[k] = m2[k] + f.m2[at] + delta * delta * cnt * wb;
+                mean[k] = fmaf(delta, wb, mean[k]);
+                sum[k] += f.sum[at];
+            }
+            cnt = nab;
+        }
+        float peak = 0.f;
+#pragma unroll
+        for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+        {
+            uint32_t wl = lane + k * 32;
+            if(wl >= n) continue;
+            size_t at = (size_t)p * n + wl;
+            dst.sum[at] = sum[k]; dst.mean[at] = mean[k]; dst.m2[at] = m2[k];
+            if(m2[k] > peak) peak = m2[k];
+        }
+        if(lane == 0) dst.filter[p] = cnt;
+        if(!bgra_sum) continue;
+        peak = warp_max(peak);
+        float acc[9];
+#pragma unroll
+        for(int i = 0; i < 9; i += 1) acc[i] = 0.f;
+#pragma unroll
+        for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+        {
+            uint32_t wl = lane + k * 32;
+            if(wl >= n) continue;
+            float v[3] = { sum[k] / cnt, mean[k], m2[k] / peak };
+#pragma unroll
+            for(int img = 0; img < 3; img += 1)
+            {
+                acc[img * 3 + 0] = fmaf(t.xw[wl], v[img], acc[img * 3 + 0]);
+                acc[img * 3 + 1] = fmaf(t.yw[wl], v[img], acc[img * 3 + 1]);
+                acc[img * 3 + 2] = fmaf(t.zw[wl], v[img], acc[img * 3 + 2]);
+            }
+        }
+#pragma unroll
+        for(int i = 0; i < 9; i += 1) acc[i] = warp_sum(acc[i]) * t.scale;
+        if(lane < 3)
+        {
+            float x = acc[lane * 3 + 0], y = acc[lane * 3 + 1], z = acc[lane * 3 + 2];
+            float ch[3] = { (2.3706743f * x) - (0.9000405f * y) - (0.4706338f * z),
+                            (-0.5138850f * x) + (1.4253036f * y) + (0.0885814f * z),
+                            (0.0052982f * x) - (0.0146949f * y) + (1.0093968f * z) };
+            uint32_t out = 0;
+#pragma unroll
+            for(int c = 0; c < 3; c += 1)
+            {
+                float q = ch[c];
+                if(!(q == q)) q = 0.f;
+                q = fminf(fmaxf(q, 0.f), 1.f);
+                out |= ((uint32_t)(q * 255.0f) & 255u) << (8 * (2 - c));
+            }
+            uint32_t *img = (lane == 0) ? bgra_sum : (lane == 1) ? bgra_mean : bgra_var;
+            img[p] = out;
+        }
+    }
+}
+
 template <int PACKED>
 __global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b)
 {
@@ -174,6 +269,16 @@ void drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream
 {
     if(packed) drt::fma_peak_kernel<1><<<grid, 256, 0, stream>>>(out, iters, 0.999f, 0.001f);
     else       drt::fma_peak_kernel<0><<<grid, 256, 0, stream>>>(out, iters, 0.999f, 0.001f);
+}
+
+void drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end,
+                                  uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream)
+{
+    drt::FilmSet set;
+    set.count = count;
+    for(int i = 0; i < count && i < 16; i += 1) set.film[i] = films[i];
+    drt::film_gather_merge_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
+                                                           bgra_sum, bgra_mean, bgra_var);
 }
 
 size_t drt_rgb_tables_bytes(void) { return sizeof(drt::RgbTables); }

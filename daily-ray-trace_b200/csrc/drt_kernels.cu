@@ -377,7 +377,9 @@ __device__ __forceinline__ float fresnel_conductor(float ir, float tr, float te,
     float eta_sq = eta * eta, kap_sq = kap * kap;
     float r = eta_sq - kap_sq - sin_sq;
     float apb_sq = sqrtf(r * r + 4.f * eta_sq * kap_sq);
-    float a = sqrtf(0.5f * (apb_sq + r));
+    /* with kappa = 0 this is sqrt(|r| + r): exactly 0 for r < 0 in IEEE arithmetic (sqrt(r*r) == |r|), but the approximate
+     * square root of the fast-math build may land one ulp low -> clamp instead of producing a NaN wavelength */
+    float a = sqrtf(fmaxf(0.5f * (apb_sq + r), 0.f));
     float s = apb_sq + cos_sq;
     float t = 2.f * a * inc_cos;
     float u = cos_sq * apb_sq + sin_sq * sin_sq;
@@ -480,7 +482,8 @@ __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT<R> &g,
                 R gq = rng.unit<R>();
                 R tan_mn = (rough * r_sqrt(f)) / r_sqrt(R(1) - f);
                 R cos_mn = R(1) / r_sqrt(R(1) + tan_mn * tan_mn);
-                R sin_mn = r_sqrt(R(1) - cos_mn * cos_mn);
+                R cm2 = cos_mn * cos_mn;
+                R sin_mn = r_sqrt((cm2 < R(1)) ? R(1) - cm2 : R(0));   /* 1/sqrt(1+t^2) may round to 1+ulp with approximate division */
                 R s, c;
                 r_sincospi(R(2) * gq, &s, &c);
                 V3<R> mn = rotate_from_z<R>(h.nrm, mk<R>(sin_mn * c, sin_mn * s, cos_mn));
@@ -1041,6 +1044,9 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                     replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, e0, c);
                     film.add(c);
                 }
+                if(L.record_dump)
+                    for(uint32_t wd = lane; wd < L.path_words; wd += DRT_WARP)
+                        L.record_dump[((size_t)cur_lp * spp + cur_s) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
                 if(L.path_dump)
                 {
 #pragma unroll

@@ -15,7 +15,8 @@ GEOMETRY_F32, GEOMETRY_F64 = 0, 1
 EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
            "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
            "drt_cuda_get_stats", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
-           "drt_cuda_measure_fp32_peak"]
+           "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
+           "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_debug_records"]
 
 
 class Film(C.Structure):
@@ -64,6 +65,14 @@ def lib():
         L.drt_cuda_film_to_rgb.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
         L.drt_cuda_film_merge.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_void_p]
+        L.drt_cuda_debug_records.argtypes = [C.c_void_p, C.POINTER(RenderParams)] + [C.c_uint32] * 4 + [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        L.drt_cuda_film_alloc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Film)]
+        L.drt_cuda_film_free.argtypes = [C.c_void_p, C.POINTER(Film)]
+        L.drt_cuda_film_ipc_export.argtypes = [C.c_void_p, C.POINTER(Film), C.c_void_p]
+        L.drt_cuda_film_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Film)]
+        L.drt_cuda_film_ipc_close.argtypes = [C.c_void_p, C.POINTER(Film)]
+        L.drt_cuda_film_merge_many.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint32, C.c_uint32,
+                                               C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.drt_cuda_measure_fp32_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -132,6 +141,15 @@ class Context:
         _check(lib().drt_cuda_sample_paths(self._h, C.byref(params), x0, y0, x1, y1, out.ctypes.data))
         return out
 
+    def debug_records(self, params, x0, y0, x1, y1):
+        """Raw path records [(pixels), spp, words] as uint32 (reinterpret floats with .view(np.float32))."""
+        words = C.c_uint32()
+        _check(lib().drt_cuda_debug_records(self._h, C.byref(params), x0, y0, x1, y1, None, 0, C.byref(words)))
+        spp = params.sample_end - params.sample_begin
+        out = np.empty(((y1 - y0) * (x1 - x0), spp, words.value), np.uint32)
+        _check(lib().drt_cuda_debug_records(self._h, C.byref(params), x0, y0, x1, y1, out.ctypes.data, out.size, C.byref(words)))
+        return out
+
     def stats(self):
         s = Stats()
         _check(lib().drt_cuda_get_stats(self._h, C.byref(s)))
@@ -142,6 +160,33 @@ class Context:
 
     def film_merge(self, dst, src, width, height, stream=None):
         _check(lib().drt_cuda_film_merge(self._h, C.byref(dst), C.byref(src), width, height, stream))
+
+    def film_alloc(self, width, height):
+        f = Film()
+        _check(lib().drt_cuda_film_alloc(self._h, width, height, C.byref(f)))
+        return f
+
+    def film_free(self, film):
+        _check(lib().drt_cuda_film_free(self._h, C.byref(film)))
+
+    def film_ipc_export(self, film):
+        buf = C.create_string_buffer(256)
+        _check(lib().drt_cuda_film_ipc_export(self._h, C.byref(film), buf))
+        return buf.raw
+
+    def film_ipc_open(self, handles):
+        f = Film()
+        _check(lib().drt_cuda_film_ipc_open(self._h, C.create_string_buffer(handles, 256), C.byref(f)))
+        return f
+
+    def film_ipc_close(self, film):
+        _check(lib().drt_cuda_film_ipc_close(self._h, C.byref(film)))
+
+    def film_merge_many(self, dst, srcs, width, height, pixel_begin, pixel_end, bgra=None, stream=None):
+        arr = (Film * len(srcs))(*srcs)
+        b = bgra or (None, None, None)
+        _check(lib().drt_cuda_film_merge_many(self._h, C.byref(dst), arr, len(srcs), width, height, pixel_begin, pixel_end,
+                                              b[0], b[1], b[2], stream))
 
     def measure_fp32_peak(self, packed=False):
         v = C.c_double()

@@ -96,6 +96,11 @@ int  drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out);
 int  drt_cuda_sample_paths(drt_cuda_context *ctx, const drt_render_params *params,
                            uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1, float *out_host);
 
+/* Diagnostics: the raw path records (the scalar weights phase 1 hands to phase 2, layout in csrc/drt_device.cuh) of the
+ * same rectangle/sample range.  With out_host == NULL only *words_per_path is returned. */
+int  drt_cuda_debug_records(drt_cuda_context *ctx, const drt_render_params *params, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
+                            float *out_host, size_t out_capacity_words, uint32_t *words_per_path);
+
 /* which = 0: sum/filter, 1: mean, 2: m2 divided by its per-pixel maximum (the three .bmp images of win32_main.c:150-152).
  * rgb_device: 3 f32 per pixel (linear RGB, may be NULL); bgra_device: packed u32 per pixel (may be NULL). */
 int  drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film_device, uint32_t width, uint32_t height, int which,
@@ -105,6 +110,27 @@ int  drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film_device, ui
  * plain addition of sum/filter).  All device pointers; src may live on a peer GPU that this device can address. */
 int  drt_cuda_film_merge(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *src_device,
                          uint32_t width, uint32_t height, void *stream);
+
+/* ---- multi-GPU: library-owned films that other processes / devices can map, and the fused merge epilogue ---- */
+
+/* Allocates the four planes of a W x H film with cudaMalloc (zero-filled) so that they can be exported over CUDA IPC. */
+int  drt_cuda_film_alloc(drt_cuda_context *ctx, uint32_t width, uint32_t height, drt_film *out_device);
+int  drt_cuda_film_free(drt_cuda_context *ctx, drt_film *film_device);
+
+/* CUDA IPC handles (64 bytes each, order sum, filter, mean, m2) of a film from drt_cuda_film_alloc, and the reverse:
+ * mapping a peer process's film into this context's address space (NVLink peer access).  Single-process callers can
+ * skip IPC and pass another device's pointers directly after cudaDeviceEnablePeerAccess. */
+int  drt_cuda_film_ipc_export(drt_cuda_context *ctx, const drt_film *film_device, unsigned char handles[4][64]);
+int  drt_cuda_film_ipc_open(drt_cuda_context *ctx, const unsigned char handles[4][64], drt_film *out_mapped);
+int  drt_cuda_film_ipc_close(drt_cuda_context *ctx, drt_film *mapped);
+
+/* ONE kernel on this device: for pixels [pixel_begin, pixel_end) read the partial films of all `count` ranks (any mix
+ * of local and peer pointers, disjoint sample sets), merge them exactly (Chan), write the merged planes to dst_device
+ * (may be peer memory, e.g. the root's film) and, if bgra_* are non-NULL, the three 8-bit images
+ * (sum/filter, mean, M2/max) for those pixels.  Callers make sure all ranks have finished rendering first. */
+int  drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *srcs_device, int count,
+                              uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
+                              uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
 
 /* Measured FP32 FMA throughput of this device (TFLOP/s, FFMA counted as 2 flops): the roofline denominator
  * MEASURED_PEAKS.json does not carry.  packed=1 uses fma.rn.f32x2. */

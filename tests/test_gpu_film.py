@@ -134,3 +134,56 @@ def test_4096_square_large_box_tiles(ctx):
         assert (_rel(got, o_sum[:, :n]).max(axis=1) <= 1e-3).mean() >= 0.98, (x0, y0)
     del film
     torch.cuda.empty_cache()
+
+
+def test_merge_many_fused_epilogue(ctx):
+    """The fused gather-merge kernel (the multi-GPU epilogue) on one device: three partial films of disjoint sample ranges
+    -> merged planes equal the single render, images equal film_to_rgb of the merged film."""
+    import torch
+    w, h, depth = 40, 24, 4
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, 96, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    dev = torch.device("cuda", 0)
+    whole = film_mod.FilmPlanes(w, h, n, dev)
+    ctx.render_device(oracledriver.params(w, h, 0, 96, depth, cfg.pixel_scheme, 9), whole.as_drt_film())
+    parts = [ctx.film_alloc(w, h) for _ in range(3)]
+    for f, (s0, s1) in zip(parts, ((0, 32), (32, 50), (50, 96))):
+        ctx.render_device(oracledriver.params(w, h, s0, s1, depth, cfg.pixel_scheme, 9), f)
+    merged = film_mod.FilmPlanes(w, h, n, dev)
+    imgs = [torch.zeros(w * h, dtype=torch.int32, device=dev) for _ in range(3)]
+    npix = w * h
+    # two calls over disjoint pixel ranges, as two ranks would issue them
+    ctx.film_merge_many(merged.as_drt_film(), parts, w, h, 0, npix // 2, bgra=[t.data_ptr() for t in imgs])
+    ctx.film_merge_many(merged.as_drt_film(), parts, w, h, npix // 2, npix, bgra=[t.data_ptr() for t in imgs])
+    torch.cuda.synchronize()
+    assert torch.equal(merged.filter, whole.filter)
+    for name in ("sum", "mean", "m2"):
+        assert _rel(getattr(merged, name).cpu().numpy(), getattr(whole, name).cpu().numpy()).max() < 2e-4, name
+    ref_img = torch.zeros(w * h, dtype=torch.int32, device=dev)
+    for which in range(3):
+        ctx.film_to_rgb(merged.as_drt_film(), w, h, which, None, ref_img.data_ptr())
+        torch.cuda.synchronize()
+        a, b = imgs[which].cpu().numpy().view(np.uint32), ref_img.cpu().numpy().view(np.uint32)
+        worst = max(np.abs(((a >> s) & 255).astype(int) - ((b >> s) & 255).astype(int)).max() for s in (0, 8, 16))
+        assert worst <= 1, which
+    for f in parts:
+        ctx.film_free(f)
+
+
+@pytest.mark.parametrize("scene", ["cornell_plane_light", "stress_all"])
+def test_large_render_is_finite(ctx, scene):
+    """67 M paths through glass, gold and mirrors: no sample may poison a pixel with NaN/inf.  (Regression: with the
+    approximate f32 sqrt, conductor Fresnel at kappa = 0 produced sqrt(-eps) for single wavelengths.)"""
+    import torch
+    w = h = 1024
+    cfg, tables, sc, cam = common.load(scene, w, h, 64, 4)
+    ctx.upload_scene(sc, cam, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    film = film_mod.FilmPlanes(w, h, sc.num_wavelengths, torch.device("cuda", 0))
+    ctx.render_device(oracledriver.params(w, h, 0, 64, 4, cfg.pixel_scheme, 5), film.as_drt_film())
+    torch.cuda.synchronize()
+    for name in ("sum", "mean", "m2"):
+        assert bool(torch.isfinite(getattr(film, name)).all()), name
+    assert float(film.sum.max()) > 0
