@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--geometry", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU film combination: fused peer-memory kernel (CUDA IPC over NVLink) or NCCL collectives")
     return ap.parse_args()
 
 
@@ -238,15 +240,49 @@ def run_b200_arm(a):
     ctx = cuda.Context(local)
     ctx.upload_scene(scene, camera, tables)
     ctx.set_geometry_precision(cuda.GEOMETRY_F64 if a.geometry == "f64" else cuda.GEOMETRY_F32)
-    film = film_mod.FilmPlanes(a.width, a.height, n, torch.device("cuda", local))
-    drt_film = film.as_drt_film()
+    dev = torch.device("cuda", local)
+    peers, merge_kind = None, "none"
+    if world > 1 and a.merge == "p2p":
+        try:
+            peers = film_mod.PeerFilmGroup(ctx, a.width, a.height)
+            merge_kind = "p2p: one fused merge+images kernel per rank over CUDA-IPC peer memory"
+        except Exception as exc:
+            print(f"[rank {rank}] peer-memory merge unavailable ({exc}); using NCCL", file=sys.stderr)
+            peers = None
+    if world > 1 and peers is None:
+        merge_kind = "nccl: 2 all_reduce + 1 reduce"
+
+    class _DevArray:   # view of library-owned device memory for torch copies (plumbing only)
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    npix_all = a.width * a.height
+    if peers is not None:
+        drt_film = peers.mine
+        film = None
+        root_planes = None
+        if rank == 0:
+            m = peers.merged
+            root_planes = {"sum": torch.as_tensor(_DevArray(m.sum, (npix_all, n)), device=dev),
+                           "filter": torch.as_tensor(_DevArray(m.filter, (npix_all,)), device=dev),
+                           "mean": torch.as_tensor(_DevArray(m.mean, (npix_all, n)), device=dev),
+                           "m2": torch.as_tensor(_DevArray(m.m2, (npix_all, n)), device=dev)}
+    else:
+        film = film_mod.FilmPlanes(a.width, a.height, n, dev)
+        drt_film = film.as_drt_film()
+        root_planes = {"sum": film.sum, "filter": film.filter, "mean": film.mean, "m2": film.m2}
+
+    def combine():
+        if peers is not None:
+            return peers.merge(stream.cuda_stream, stream.synchronize)
+        return film_mod.merge_distributed_(film)
     stream = torch.cuda.current_stream()
     prm = common.structs.RenderParams(a.width, a.height, rank * a.spp, (rank + 1) * a.spp, a.depth, cfg.pixel_scheme, a.seed)
     paths_per_step = a.width * a.height * a.spp * world
 
     def step():
         ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
-        return film_mod.merge_distributed_(film)
+        return combine()
 
     def fence():
         torch.cuda.synchronize()
@@ -269,8 +305,8 @@ def run_b200_arm(a):
         k_start[i].record(stream)
         ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
         k_stop[i].record(stream)
-        film_mod.merge_distributed_(film)
-        launches += 1
+        combine()
+        launches += 1 + (1 if peers is not None else 0)
     e1.record(stream)
     fence()
     t1 = time.perf_counter()
@@ -294,10 +330,10 @@ def run_b200_arm(a):
             ctx.render_host_into(prm, host_film)           # the C-ABI host-buffer call of include/drt_cuda.h
         else:
             ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
-            film_mod.merge_distributed_(film)
+            combine()
             if rank == 0:
                 for k in ("sum", "filter", "mean", "m2"):
-                    pinned[k].copy_(getattr(film, k), non_blocking=True)
+                    pinned[k].copy_(root_planes[k], non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_step()
@@ -329,7 +365,7 @@ def run_b200_arm(a):
             "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "impl": "b200",
             "data": f"shipped scene assets/scenes/{a.scene}.scn through the legacy-compat parser; per-path Philox4x32-10 streams, seed {a.seed}",
-            "config": {"workload": workload_name(a), "geometry": a.geometry,
+            "config": {"workload": workload_name(a), "geometry": a.geometry, "film_merge": merge_kind,
                        "l2": "inputs (scene + spectra, < 64 KB) live in shared memory; each step writes 4 fresh film planes "
                              f"({film_bytes / 1e6:.0f} MB > 126 MB L2), nothing is re-read between steps",
                        "samples_per_pixel_total": a.spp * world},
@@ -366,6 +402,8 @@ def run_b200_arm(a):
             except Exception as exc:   # the baseline is reported, never a gate
                 line["cpu_baseline"] = {"value": None, "unit": "paths/s", "cores": _cpu_cores(), "kind": "unavailable", "sample": repr(exc)}
         print(json.dumps(line), flush=True)
+    if peers is not None:
+        peers.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

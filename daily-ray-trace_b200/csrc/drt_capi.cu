@@ -497,6 +497,51 @@ extern "C" int drt_cuda_film_ipc_close(drt_cuda_context *ctx, drt_film *mapped)
     return DRT_CUDA_OK;
 }
 
+extern "C" int drt_cuda_buffer_alloc(drt_cuda_context *ctx, size_t bytes, void **out)
+{
+    if(!ctx || !out || bytes == 0) return fail(DRT_CUDA_E_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(out, bytes));
+    CU(cudaMemset(*out, 0, bytes));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_buffer_free(drt_cuda_context *ctx, void *ptr)
+{
+    if(!ctx) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(ptr));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_buffer_ipc_export(drt_cuda_context *ctx, const void *ptr, unsigned char handle[64])
+{
+    if(!ctx || !ptr || !handle) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+    memcpy(handle, &h, 64);
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_buffer_ipc_open(drt_cuda_context *ctx, const unsigned char handle[64], void **out)
+{
+    if(!ctx || !handle || !out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_buffer_ipc_close(drt_cuda_context *ctx, void *mapped)
+{
+    if(!ctx || !mapped) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(mapped));
+    return DRT_CUDA_OK;
+}
+
 extern "C" int drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *dst, const drt_film *srcs, int count, uint32_t width, uint32_t height,
                                         uint64_t pixel_begin, uint64_t pixel_end, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream)
 {

@@ -16,7 +16,8 @@ EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "d
            "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
            "drt_cuda_get_stats", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
-           "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_debug_records"]
+           "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
+           "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close"]
 
 
 class Film(C.Structure):
@@ -66,6 +67,11 @@ def lib():
                                            C.c_void_p, C.c_void_p]
         L.drt_cuda_film_merge.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_void_p]
         L.drt_cuda_debug_records.argtypes = [C.c_void_p, C.POINTER(RenderParams)] + [C.c_uint32] * 4 + [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        L.drt_cuda_buffer_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.drt_cuda_buffer_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.drt_cuda_buffer_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.drt_cuda_buffer_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.drt_cuda_buffer_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         L.drt_cuda_film_alloc.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Film)]
         L.drt_cuda_film_free.argtypes = [C.c_void_p, C.POINTER(Film)]
         L.drt_cuda_film_ipc_export.argtypes = [C.c_void_p, C.POINTER(Film), C.c_void_p]
@@ -160,6 +166,27 @@ class Context:
 
     def film_merge(self, dst, src, width, height, stream=None):
         _check(lib().drt_cuda_film_merge(self._h, C.byref(dst), C.byref(src), width, height, stream))
+
+    def buffer_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().drt_cuda_buffer_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def buffer_free(self, ptr):
+        _check(lib().drt_cuda_buffer_free(self._h, ptr))
+
+    def buffer_ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        _check(lib().drt_cuda_buffer_ipc_export(self._h, ptr, buf))
+        return buf.raw
+
+    def buffer_ipc_open(self, handle):
+        p = C.c_void_p()
+        _check(lib().drt_cuda_buffer_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def buffer_ipc_close(self, ptr):
+        _check(lib().drt_cuda_buffer_ipc_close(self._h, ptr))
 
     def film_alloc(self, width, height):
         f = Film()

@@ -61,3 +61,66 @@ def merge_distributed_(film, root=0, group=None):
     dist.reduce(film.m2, dst=root, op=dist.ReduceOp.SUM, group=group)
     film.mean.copy_(mean_tot)
     return 3
+
+
+class PeerFilmGroup:
+    """The fused multi-GPU epilogue over peer memory (drt_cuda_film_merge_many): every rank owns a library-allocated partial
+    film; all partial films, the root's merged film and the root's three BGRA images are mapped into every process through
+    CUDA IPC once, then each step every rank runs ONE kernel over its pixel slice that reads all partial films over
+    NVLink, merges them exactly and writes merged planes + images straight into the root's memory.
+    torch.distributed is used only to exchange the 64-byte handles and for the two host barriers around the kernel."""
+
+    def __init__(self, ctx, width, height, root=0, group=None):
+        self.ctx, self.width, self.height, self.root, self.group = ctx, width, height, root, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        npix = width * height
+        self.mine = ctx.film_alloc(width, height)
+        self.merged = ctx.film_alloc(width, height) if self.rank == root else None
+        self.images = ctx.buffer_alloc(3 * npix * 4) if self.rank == root else None
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ctx.film_ipc_export(self.mine), group=group)
+        rooted = [(ctx.film_ipc_export(self.merged), ctx.buffer_ipc_export(self.images)) if self.rank == root else None]
+        dist.broadcast_object_list(rooted, src=root, group=group)
+        self._opened = []
+        self.films = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.films.append(self.mine)
+            else:
+                f = ctx.film_ipc_open(handles[r])
+                self._opened.append(f)
+                self.films.append(f)
+        if self.rank == root:
+            self.dst, self.img_base = self.merged, self.images
+        else:
+            self.dst = ctx.film_ipc_open(rooted[0][0])
+            self._opened.append(self.dst)
+            self.img_base = ctx.buffer_ipc_open(rooted[0][1])
+        self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
+        self.bgra = [self.img_base + i * npix * 4 for i in range(3)]
+        dist.barrier(group=group)
+
+    def merge(self, stream_ptr=None, sync=None):
+        """Call after this rank's render was enqueued.  `sync` = callable that waits for this rank's stream."""
+        sync()
+        dist.barrier(group=self.group)          # every rank's partial film is complete
+        self.ctx.film_merge_many(self.dst, self.films, self.width, self.height, self.p0, self.p1, bgra=self.bgra, stream=stream_ptr)
+        sync()
+        dist.barrier(group=self.group)          # the root's merged film and images are complete
+        return 1
+
+    def close(self):
+        for f in self._opened:
+            try:
+                self.ctx.film_ipc_close(f)
+            except Exception:
+                pass
+        if self.rank != self.root:
+            try:
+                self.ctx.buffer_ipc_close(self.img_base)
+            except Exception:
+                pass
+        self.ctx.film_free(self.mine)
+        if self.merged is not None:
+            self.ctx.film_free(self.merged)
+            self.ctx.buffer_free(self.images)

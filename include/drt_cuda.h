@@ -124,6 +124,13 @@ int  drt_cuda_film_ipc_export(drt_cuda_context *ctx, const drt_film *film_device
 int  drt_cuda_film_ipc_open(drt_cuda_context *ctx, const unsigned char handles[4][64], drt_film *out_mapped);
 int  drt_cuda_film_ipc_close(drt_cuda_context *ctx, drt_film *mapped);
 
+/* Plain device buffers that can be shared the same way (e.g. the root's three BGRA images). */
+int  drt_cuda_buffer_alloc(drt_cuda_context *ctx, size_t bytes, void **out_device);
+int  drt_cuda_buffer_free(drt_cuda_context *ctx, void *device_ptr);
+int  drt_cuda_buffer_ipc_export(drt_cuda_context *ctx, const void *device_ptr, unsigned char handle[64]);
+int  drt_cuda_buffer_ipc_open(drt_cuda_context *ctx, const unsigned char handle[64], void **out_mapped);
+int  drt_cuda_buffer_ipc_close(drt_cuda_context *ctx, void *mapped);
+
 /* ONE kernel on this device: for pixels [pixel_begin, pixel_end) read the partial films of all `count` ranks (any mix
  * of local and peer pointers, disjoint sample sets), merge them exactly (Chan), write the merged planes to dst_device
  * (may be peer memory, e.g. the root's film) and, if bgra_* are non-NULL, the three 8-bit images
