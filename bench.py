@@ -25,7 +25,14 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 PKG = "daily-ray-trace_b200"
-SCRATCH = os.path.join(REPO, "gpurun_out", "bench_scratch")
+import atexit
+import shutil
+import tempfile
+SCRATCH = os.environ.get("DRT_BENCH_SCRATCH") or tempfile.mkdtemp(prefix="drt_bench_")
+os.environ["DRT_BENCH_SCRATCH"] = SCRATCH          # pool workers (spawned) share the parent's directory
+if os.environ.get("DRT_BENCH_SCRATCH_OWNER") is None:
+    os.environ["DRT_BENCH_SCRATCH_OWNER"] = str(os.getpid())
+    atexit.register(lambda: shutil.rmtree(SCRATCH, ignore_errors=True))
 
 
 def parse_args():

@@ -107,9 +107,9 @@ DEFAULT_CONFIG_TEXT = """num_pixel_samples {spp}
 max_cast_depth    {depth}
 output_width      {width}
 output_height     {height}
-min_wl            380.0
-max_wl            720.0
-wl_interval       5.0
+min_wl            {min_wl}
+max_wl            {max_wl}
+wl_interval       {wl_interval}
 pixel_scheme      {scheme}
 input_scene       {scene}
 output_spd        output\\output.spd
@@ -131,6 +131,8 @@ yellow_spd        spectra\\yellow_rgb_to_spd.csv
 """
 
 
-def make_config_text(scene="scenes\\cornell_plane_light.scn", width=64, height=64, spp=1, depth=4, scheme="pixel_random"):
+def make_config_text(scene="scenes\\cornell_plane_light.scn", width=64, height=64, spp=1, depth=4, scheme="pixel_random",
+                     min_wl=380.0, max_wl=720.0, wl_interval=5.0):
     """A config.cfg in the reference's own format (config.cfg:1-25) for the given workload."""
-    return DEFAULT_CONFIG_TEXT.format(scene=scene, width=width, height=height, spp=spp, depth=depth, scheme=scheme)
+    return DEFAULT_CONFIG_TEXT.format(scene=scene, width=width, height=height, spp=spp, depth=depth, scheme=scheme,
+                                      min_wl=f"{min_wl:.1f}", max_wl=f"{max_wl:.1f}", wl_interval=f"{wl_interval:.1f}")

@@ -18,9 +18,9 @@ def scene_path(name):
     raise FileNotFoundError(name)
 
 
-def load(name, width, height, spp=1, depth=4, scheme="pixel_random"):
+def load(name, width, height, spp=1, depth=4, scheme="pixel_random", **grid):
     """Returns (config, tables, scene, camera) for a shipped or golden scene."""
-    cfg = host.parse_config_text(host.make_config_text(width=width, height=height, spp=spp, depth=depth, scheme=scheme))
+    cfg = host.parse_config_text(host.make_config_text(width=width, height=height, spp=spp, depth=depth, scheme=scheme, **grid))
     tables = host.load_tables(cfg, ASSETS)
     parsed = host.parse_scene_text(open(scene_path(name)).read())
     scene, camera = host.build_scene(parsed, tables, ASSETS, width, height)

@@ -1,0 +1,112 @@
+"""GPU tier: the other wavelength grids (kernel instantiations with 1, 2 and 4 wavelength slots per lane), the limits of
+the scene format (16 surfaces, many lights, deep paths) and the error behaviour of the C ABI."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import common
+import oracledriver
+
+cuda = importlib.import_module("daily-ray-trace_b200.cuda")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cuda.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("interval,expect_n", [(20.0, 18), (10.0, 35), (5.0, 69), (3.0, 114)])
+def test_wavelength_grids(ctx, interval, expect_n):
+    """N = (max-min)/interval + 1 (spectrum.c:3): 18, 35, 69 and 114 wavelengths -> 1, 2, 3 and 4 slots per lane."""
+    w, h, spp = 32, 24, 6
+    cfg, tables, scene, camera = common.load("stress_all", w, h, spp, 4, wl_interval=interval)
+    assert scene.num_wavelengths == expect_n
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    prm = oracledriver.params(w, h, 0, spp, 4, cfg.pixel_scheme, 21)
+    gpu = ctx.sample_paths(prm, 0, 0, w, h)
+    film = ctx.render_host(prm)
+    o_sum, o_avg, o_m2, o_paths, _ = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h, want_paths=True)
+    assert gpu.shape[-1] == expect_n
+    assert (common.path_errors(gpu, o_paths) <= 1e-4).mean() >= 0.995
+    ref = o_sum[:, :expect_n]
+    rel = np.abs(film["sum"] - ref) / np.maximum(np.abs(ref), 1e-5 * np.abs(ref).max())
+    assert (rel.max(axis=1) <= 2e-3).mean() >= 0.99
+
+
+def _many_surfaces_scene(n_lights):
+    """16 surfaces (the format's limit, read_scene.h:85-86): a floor, 15 - n_lights diffuse spheres and n_lights sphere lights."""
+    out = ["Camera\nposition 0.0, 2.0, 9.0\ntarget 0.0, 0.0, 0.0\nroll 0.0\nfov 70.0\nfdepth 6.0\nflength 0.3\naperture 0.0\n",
+           "Material\nname vacuum\nrefract constant 1.0\nbase_material\n", "Material\nname escape\nescape_material\n",
+           "Material\nname grey\ndiffuse rgb 0.6, 0.6, 0.6\nglossy rgb 0.2, 0.2, 0.2\nshininess 30.0\nbdsfs bp_diffuse_bdsf, bp_glossy_bdsf\ndir_func cos_weighted_sample_hemisphere\n",
+           "Material\nname lamp\nemission constant 0.4\nis_black_body true\n",
+           "Surface\nname floor\ntype plane\nposition -6.0, -1.0, -6.0\npointu 6.0, -1.0, -6.0\npointv -6.0, -1.0, 6.0\nmaterial grey\n"]
+    for i in range(15):
+        x, z = -4.0 + 2.0 * (i % 5), -3.0 + 2.5 * (i // 5)
+        if i < n_lights:
+            out.append(f"Surface\nname l{i}\ntype sphere\nposition {x:.1f}, 3.0, {z:.1f}\nradius 0.3\nmaterial lamp\n")
+        else:
+            out.append(f"Surface\nname s{i}\ntype sphere\nposition {x:.1f}, 0.0, {z:.1f}\nradius 0.8\nmaterial grey\n")
+    return "\n".join(out)
+
+
+@pytest.mark.parametrize("n_lights,depth", [(1, 4), (4, 3), (12, 2)])
+def test_sixteen_surfaces_many_lights(ctx, host, n_lights, depth):
+    """Multi-light next-event estimation (the running-sum quirk Q4) with up to 12 sphere lights, 16 surfaces."""
+    w, h, spp = 24, 16, 4
+    cfg = host.parse_config_text(host.make_config_text(width=w, height=h, spp=spp, depth=depth))
+    tables = host.load_tables(cfg, common.ASSETS)
+    scene, camera = host.build_scene(host.parse_scene_text(_many_surfaces_scene(n_lights)), tables, common.ASSETS, w, h)
+    assert scene.num_surfaces == 16
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 8)
+    gpu = ctx.sample_paths(prm, 0, 0, w, h)
+    _, _, _, o_paths, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h, want_paths=True)
+    st = ctx.stats()
+    assert st.shadow_rays == cnt.shadow_rays == st.shaded_bounces * n_lights
+    assert (common.path_errors(gpu, o_paths) <= 2e-4).mean() >= 0.99
+
+
+def test_deep_paths(ctx):
+    """max_cast_depth 12: records of 8 warps no longer fit in shared memory, the launcher drops to fewer warps per CTA."""
+    w, h, spp, depth = 24, 16, 3, 12
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, spp, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 4)
+    gpu = ctx.sample_paths(prm, 0, 0, w, h)
+    _, _, _, o_paths, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h, want_paths=True)
+    assert ctx.stats().reached_depth_cap == cnt.reached_depth_cap
+    assert (common.path_errors(gpu, o_paths) <= 1e-3).mean() >= 0.99
+
+
+def test_error_codes(ctx):
+    L = cuda.lib()
+    w, h = 16, 16
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, 2, 4)
+    fresh = cuda.Context(0)
+    with pytest.raises(cuda.CudaError) as e:          # render before upload_scene
+        fresh.render_host(oracledriver.params(w, h, 0, 2))
+    assert e.value.code == -105
+    fresh.close()
+    ctx.upload_scene(scene, camera, tables)
+    for bad in (oracledriver.params(w, h, 3, 3), oracledriver.params(w, h, 0, 2, 0), oracledriver.params(0, h, 0, 2)):
+        with pytest.raises(cuda.CudaError) as e:
+            ctx.render_host(bad)
+        assert e.value.code == -103
+    with pytest.raises(cuda.CudaError) as e:          # depth x lights beyond what shared memory can hold: loud, not silent
+        ctx.sample_paths(oracledriver.params(w, h, 0, 1, 4000), 0, 0, 1, 1)
+    assert e.value.code == -104 and b"shared memory" in L.drt_cuda_last_error()
+    with pytest.raises(cuda.CudaError):
+        cuda.Context(99)
+    # a scene whose wavelength grid does not contain 630 nm cannot be rendered (trans_wl, daily_ray_trace.c:381)
+    cfg2, tables2, scene2, camera2 = common.load("cornell_plane_light", w, h, 1, 4, min_wl=380.0, max_wl=600.0, wl_interval=5.0)
+    with pytest.raises(cuda.CudaError) as e:
+        ctx.upload_scene(scene2, camera2, tables2)
+    assert e.value.code == -104
