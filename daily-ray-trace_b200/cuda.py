@@ -127,9 +127,10 @@ class Context:
 
     def render_host(self, params):
         """End-to-end call with host buffers: returns dict of numpy f32 arrays sum[H*W,N], filter[H*W], mean, m2."""
-        npix = params.width * params.height
-        out = {"sum": np.empty((npix, self.n), np.float32), "filter": np.empty(npix, np.float32),
-               "mean": np.empty((npix, self.n), np.float32), "m2": np.empty((npix, self.n), np.float32)}
+        npix = max(params.width * params.height, 1)
+        n = self.n or 1     # before upload_scene the library reports DRT_CUDA_E_STATE; buffers only need to exist
+        out = {"sum": np.empty((npix, n), np.float32), "filter": np.empty(npix, np.float32),
+               "mean": np.empty((npix, n), np.float32), "m2": np.empty((npix, n), np.float32)}
         film = Film(out["sum"].ctypes.data, out["filter"].ctypes.data, out["mean"].ctypes.data, out["m2"].ctypes.data)
         _check(lib().drt_cuda_render_host(self._h, C.byref(params), C.byref(film)))
         return out
