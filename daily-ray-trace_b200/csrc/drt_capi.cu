@@ -206,7 +206,11 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     /* spectrum pool: row 0 = zeros, then one row per SPD a material was given */
     SpdIndex index;
     memset(&index, 0, sizeof(index));
-    index.n = n; index.nslots = (n + 31) / 32; index.npad = index.nslots * 32;
+    /* slots per lane of a half warp (16 lanes): the render kernel is instantiated for 2, 3, 5 and 8 */
+    int half_slots = (n + 15) / 16;
+    half_slots = half_slots <= 2 ? 2 : half_slots <= 3 ? 3 : half_slots <= 5 ? 5 : 8;
+    index.n = n; index.nslots = half_slots; index.npad = ((n + 31) / 32) * 32;
+    if(index.npad < half_slots * 16) index.npad = half_slots * 16;
     std::vector<float> pool((size_t)index.npad, 0.f);
     int rows = 1;
     for(int m = 0; m < scene->num_materials; m += 1)

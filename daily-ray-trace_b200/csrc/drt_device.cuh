@@ -13,7 +13,9 @@
 #include "drt_scene.h"
 
 #define DRT_WARP 32
-#define DRT_MAX_SLOTS 4            /* ceil(DRT_MAX_WAVELENGTHS / 32) */
+#define DRT_MAX_SLOTS 4            /* ceil(DRT_MAX_WAVELENGTHS / 32): full-warp wavelength layout of the film epilogue kernels */
+#define DRT_HALF 16                /* phase 2 of the render kernel: a path is shaded by a HALF warp, lane l16 holds wavelengths l16 + 16k */
+#define DRT_MAX_HALF_SLOTS 8       /* ceil(DRT_MAX_WAVELENGTHS / 16) */
 #define DRT_CTA_WARPS 8
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 

@@ -9,8 +9,9 @@
  *                     shared memory (K2), light sampling + shadow rays (K3), direction sampling (K4).  All spectral
  *                     quantities are reduced to a handful of scalar WEIGHTS per BSDF evaluation (eval_weights) and
  *                     written as a compact path record to shared memory.
- *   phase 2 "shade"   one WARP per path, wavelengths across lanes (3 slots per lane for N = 69).  The record is
- *                     broadcast, spectra are conflict-free shared-memory rows, throughput / radiance live in registers,
+ *   phase 2 "shade"   one HALF WARP per path, wavelengths across its 16 lanes (5 slots per lane for N = 69), two paths per
+ *                     warp at a time.  The record is a broadcast read, spectra are conflict-free shared-memory rows,
+ *                     throughput / radiance live in registers,
  *                     and the pixel's film (sum, Welford mean and M2, daily_ray_trace.c:732-743) stays in registers
  *                     for ALL samples of the pixel: each film plane is written to HBM exactly once, coalesced (K6).
  *
@@ -547,7 +548,7 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 #define HDR_FAST 4u
 
 /* ------------------------------------------------------------------ phase 1: trace one path, emit its record
- * `rec` points at this lane's column (word w at rec[w*32]).  Returns the termination-histogram bin. */
+ * `rec` points at this lane's column (word w at rec[w*32]).  Returns the termination-histogram bin and a class bit. */
 
 template <typename R>
 __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec,
@@ -586,7 +587,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     }
     rec[REC_VIG * DRT_WARP] = (float)dot(d, fwd);   /* Q20 */
 
-    uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth;
+    uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth, general = 0;
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
     for(uint32_t depth = 0; depth < L.max_depth; depth += 1)
     {
@@ -656,6 +657,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         if(g.bmask[h.surf_mat] == BMASK_PLASTIC && g.nlobes[h.surf_mat] == 2 && g.nlights == 1)
             hdr = KIND_SHADE | HDR_FAST | ((vis_mask & 1u) << 3) | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_DIFFUSE] << 4)
                   | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_GLOSSY] << 18);
+        else general = 1;
         rec[base * DRT_WARP] = __uint_as_float(hdr);
         rec[(base + 1) * DRT_WARP] = (float)h.on_dot;
         nb += 1;
@@ -664,7 +666,8 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     }
     rec[REC_NB * DRT_WARP] = __uint_as_float(nb);
     tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
-    return (end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8;   /* histogram bin: depth of termination, 8 = hit the cap */
+    /* bits 0-7: histogram bin (depth of termination, 8 = hit the cap); bit 8: the record has a bounce that needs the general shader */
+    return ((end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8) | (general << 8);
 }
 
 /* ------------------------------------------------------------------ packed f32x2 arithmetic (sm_100 fma.rn.f32x2)
@@ -718,61 +721,62 @@ template <int NS> __device__ __forceinline__ void v_sub(float (&o)[NS], const fl
     v_add<NS>(o, a, nb);
 }
 
-/* ------------------------------------------------------------------ phase 2: spectral replay of one record by a warp
+/* ------------------------------------------------------------------ phase 2: spectral replay of one record by a HALF warp
  *
- * Lane l holds wavelengths l, l+32, ... (NS register slots).  `col` is the record column of the path (word w at
+ * A path is shaded by 16 lanes: lane l16 = lane & 15 holds wavelengths l16, l16+16, ... (NS register slots; 5 for N = 69,
+ * 86 % of the slots carry a wavelength against 72 % for a 32-lane layout), and the two halves of a warp replay two
+ * paths at once, sharing every address, header-decode and loop instruction.  `col` is the record column of the path (word w at
  * col[w*32]); every read of it is a shared-memory broadcast.  SpdIndex.row holds WORD OFFSETS into the pool. */
 
 template <int NS> struct Spec { float v[NS]; };
 template <int NS> struct ShadeState { Spec<NS> thr, dst; };
 
-/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform.  Out of line and
- * written so that each Fresnel formula is instantiated once: this code is cold for the shipped walls but must stay small
- * enough not to evict the hot path from the instruction cache when a scene does use mirrors, glass or metals. */
-template <int NS>
-__device__ __noinline__ Spec<NS> eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
-                                                       int surf_mat, int inc_mat, int trans_mat, float on_dot)
+/* All seven spectral bases at ONE wavelength (table values d, g, m; refraction/extinction ir, tr, te).  Out of line and
+ * scalar, so the Fresnel formulas exist once in the kernel however many wavelength slots a lane holds: this code is cold
+ * for the shipped walls but must stay small enough not to evict the hot path from the instruction cache. */
+struct EvalWeights { float w_const, w_d, w_g, w_m, w_r, w_a, c_a, w_b, c_b, on_dot; };
+
+__device__ __noinline__ float eval_general_one(EvalWeights e, float d, float g, float m, float ir, float tr, float te)
 {
-    Spec<NS> f;
-    float base = 0.f;
-    if(mask & (1 << BK_CONST)) { base = col[at * DRT_WARP]; at += 1; }
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) f.v[k] = base;
-    /* the three table lobes share one multiply-add loop: (weight, row) pairs in mask order */
+    float f = e.w_const;
+    f = fmaf(e.w_d, d, f);
+    f = fmaf(e.w_g, g, f);
+    f = fmaf(e.w_m, m, f);
+    if(e.w_r != 0.f) f = fmaf(e.w_r, fresnel_dielectric<float>(ir, tr, e.on_dot), f);
 #pragma unroll 1
-    for(int kind = BK_DIFFUSE; kind <= BK_MIRROR; kind += 1)
+    for(int t = 0; t < 2; t += 1)   /* F(on_dot) of fs_conductor_bdsf, F(mn_dot) of ct_conductor_bdsf: one loop body */
     {
-        if(!(mask & (1 << kind))) continue;
-        float w = col[at * DRT_WARP]; at += 1;
-        int spd = (kind == BK_DIFFUSE) ? DRT_SPD_DIFFUSE : (kind == BK_GLOSSY) ? DRT_SPD_GLOSSY : DRT_SPD_MIRROR;
-        const float *row = pool_lane + ix.row[surf_mat][spd];
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, row[k * DRT_WARP], f.v[k]);
+        float w = t ? e.w_b : e.w_a, cs = t ? e.c_b : e.c_a;
+        if(w != 0.f) f = fmaf(w, fresnel_conductor(ir, tr, te, cs), f);
     }
+    return f;
+}
+
+/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform. */
+template <int NS>
+__device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
+                                                          int surf_mat, int inc_mat, int trans_mat, float on_dot)
+{
+    EvalWeights e;
+    e.w_const = e.w_d = e.w_g = e.w_m = e.w_r = e.w_a = e.c_a = e.w_b = e.c_b = 0.f;
+    e.on_dot = on_dot;
+    if(mask & (1 << BK_CONST))   { e.w_const = col[at * DRT_WARP]; at += 1; }
+    if(mask & (1 << BK_DIFFUSE)) { e.w_d = col[at * DRT_WARP]; at += 1; }
+    if(mask & (1 << BK_GLOSSY))  { e.w_g = col[at * DRT_WARP]; at += 1; }
+    if(mask & (1 << BK_MIRROR))  { e.w_m = col[at * DRT_WARP]; at += 1; }
+    if(mask & (1 << BK_DIEL_R))  { e.w_r = col[at * DRT_WARP]; at += 1; }
+    if(mask & (1 << BK_COND_ON)) { e.w_a = col[at * DRT_WARP]; e.c_a = on_dot; at += 1; }
+    if(mask & (1 << BK_COND_MN)) { e.w_b = col[at * DRT_WARP]; e.c_b = col[(at + 1) * DRT_WARP]; }
+    const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];     /* absent spectra point at the all-zero row */
+    const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
+    const float *mr = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
     const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT];
     const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT];
     const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT];
-    if(mask & (1 << BK_DIEL_R))
-    {
-        float w = col[at * DRT_WARP]; at += 1;
-        if(w != 0.f)
-        {
+    Spec<NS> f;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_dielectric<float>(ir[k * DRT_WARP], tr[k * DRT_WARP], on_dot), f.v[k]);
-        }
-    }
-    /* conductor terms: F(on_dot) of fs_conductor_bdsf and/or F(mn_dot) of ct_conductor_bdsf, one loop body for both */
-    float w_a = 0.f, c_a = 0.f, w_b = 0.f, c_b = 0.f;
-    if(mask & (1 << BK_COND_ON)) { w_a = col[at * DRT_WARP]; c_a = on_dot; at += 1; }
-    if(mask & (1 << BK_COND_MN)) { w_b = col[at * DRT_WARP]; c_b = col[(at + 1) * DRT_WARP]; }
-#pragma unroll 1
-    for(int t = 0; t < 2; t += 1)
-    {
-        float w = t ? w_b : w_a, cs = t ? c_b : c_a;
-        if(w == 0.f) continue;
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_conductor(ir[k * DRT_WARP], tr[k * DRT_WARP], te[k * DRT_WARP], cs), f.v[k]);
-    }
+    for(int k = 0; k < NS; k += 1)
+        f.v[k] = eval_general_one(e, dr[k * DRT_HALF], gr[k * DRT_HALF], mr[k * DRT_HALF], ir[k * DRT_HALF], tr[k * DRT_HALF], te[k * DRT_HALF]);
     return f;
 }
 
@@ -799,7 +803,7 @@ __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, ui
         float kk = col[(e + ew) * DRT_WARP];
         const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_WARP]) * kk;   /* Q4 */
+        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_HALF]) * kk;   /* Q4 */
     }
 #pragma unroll
     for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], contrib[k], st.dst.v[k]);
@@ -834,7 +838,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
             const float *gr = pool_lane + (hdr >> 18);
             float d_row[NS], g_row[NS];
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_WARP]; g_row[k] = gr[k * DRT_WARP]; }
+            for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_HALF]; g_row[k] = gr[k * DRT_HALF]; }
             const float wd_n = p[2 * DRT_WARP], wg_n = p[3 * DRT_WARP], kk = p[(2 + ew) * DRT_WARP];
             const float wd_s = p[(3 + ew) * DRT_WARP], wg_s = p[(4 + ew) * DRT_WARP];
             float f[NS], t[NS];
@@ -855,7 +859,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
         {
             const float *row = pool_lane + ix.row[(hdr >> 3) & 31][DRT_SPD_EMISSION];
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], row[k * DRT_WARP], st.dst.v[k]);
+            for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], row[k * DRT_HALF], st.dst.v[k]);
             break;
         }
         st = shade_bounce_general<NS, G>(col, base, hdr, g, ix, pool_lane, ew, L.nlights, st);
@@ -865,11 +869,12 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
     for(int k = 0; k < NS; k += 1) c[k] = st.dst.v[k] * vig;
 }
 
-/* film of one pixel held by a warp: lane l owns wavelengths l, l+32, ... */
+/* film of one pixel held by a half warp: lane l16 owns wavelengths l16, l16+16, ...; when both halves work on the same
+ * pixel each holds the partial film of its samples and merge_halves() combines them (Chan et al.) before the store */
 template <int NS> struct PixelFilm
 {
     float sum[NS], mean[NS], m2[NS], cnt;
-    bool  lit;      /* some sample of this pixel was non-zero (warp-uniform) */
+    bool  lit;      /* some sample of this pixel was non-zero (uniform within the half warp) */
     __device__ __forceinline__ void clear()
     {
         cnt = 0.f; lit = false;
@@ -902,18 +907,41 @@ template <int NS> struct PixelFilm
             m2[k] = fmaf(delta, -mean[k], m2[k]);
         }
     }
+    /* this half <- this half (+) the other half: count, mean, M2 by the pairwise update, sums added */
+    __device__ __forceinline__ void merge_halves()
+    {
+        float nb = __shfl_xor_sync(0xffffffffu, cnt, DRT_HALF);
+        bool  lb = __shfl_xor_sync(0xffffffffu, (int)lit, DRT_HALF) != 0;
+        float nab = cnt + nb;
+        float wb = (nab > 0.f) ? nb / nab : 0.f;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            float mb = __shfl_xor_sync(0xffffffffu, mean[k], DRT_HALF);
+            float vb = __shfl_xor_sync(0xffffffffu, m2[k], DRT_HALF);
+            float sb = __shfl_xor_sync(0xffffffffu, sum[k], DRT_HALF);
+            float delta = mb - mean[k];
+            m2[k] = m2[k] + vb + delta * delta * cnt * wb;
+            mean[k] = fmaf(delta, wb, mean[k]);
+            sum[k] += sb;
+        }
+        cnt = nab; lit = lit || lb;
+    }
 };
 
-/* film <-> HBM, once per pixel per render: out of line (cold relative to the per-sample code) and by value */
+/* film <-> HBM, once per pixel per render: out of line (cold relative to the per-sample code) and by value.
+ * Only the lower half warp (lanes 0-15) touches memory. */
 template <int NS>
 __device__ __noinline__ PixelFilm<NS> film_load(FilmPtrs film, uint32_t gpix, uint32_t n, uint32_t lane)
 {
     PixelFilm<NS> f;
+    f.clear();
+    if(lane >= DRT_HALF) return f;
     f.cnt = film.filter[gpix]; f.lit = true;
 #pragma unroll
     for(int k = 0; k < NS; k += 1)
     {
-        uint32_t wl = lane + k * DRT_WARP;
+        uint32_t wl = lane + k * DRT_HALF;
         size_t at = (size_t)gpix * n + wl;
         f.sum[k] = (wl < n) ? film.sum[at] : 0.f; f.mean[k] = (wl < n) ? film.mean[at] : 0.f; f.m2[k] = (wl < n) ? film.m2[at] : 0.f;
     }
@@ -923,10 +951,11 @@ __device__ __noinline__ PixelFilm<NS> film_load(FilmPtrs film, uint32_t gpix, ui
 template <int NS>
 __device__ __noinline__ void film_store(FilmPtrs film, uint32_t gpix, uint32_t n, uint32_t lane, PixelFilm<NS> f)
 {
+    if(lane >= DRT_HALF) return;
 #pragma unroll
     for(int k = 0; k < NS; k += 1)
     {
-        uint32_t wl = lane + k * DRT_WARP;
+        uint32_t wl = lane + k * DRT_HALF;
         if(wl < n)
         {
             size_t at = (size_t)gpix * n + wl;
@@ -968,17 +997,21 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     const SpdIndex &ix = *six;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lane16 = lane & (DRT_HALF - 1), half = lane >> 4;
     float *rec = srec + (size_t)warp * L.path_words * DRT_WARP;
-    const float *pool_lane = spool + lane;
+    const float *pool_lane = spool + lane16;
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
     const uint32_t n = (uint32_t)ix.n;
     const uint32_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
     const bool have_film = L.film.sum != nullptr;
+    /* one pixel per task (spp >= 32): both half warps shade samples of that pixel, two paths at a time.
+     * several pixels per task (spp < 32): the lower half walks all slots and handles the pixel boundaries alone. */
+    const bool paired = L.pixels_per_task == 1;
 
     float e0[NS];   /* emission of light 0, kept in registers for the whole kernel */
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) e0[k] = (L.nlights > 0) ? pool_lane[ix.row[g.mat[g.light_surf[0]]][DRT_SPD_EMISSION] + k * DRT_WARP] : 0.f;
+    for(int k = 0; k < NS; k += 1) e0[k] = (L.nlights > 0) ? pool_lane[ix.row[g.mat[g.light_surf[0]]][DRT_SPD_EMISSION] + k * DRT_HALF] : 0.f;
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
     uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
@@ -1003,12 +1036,13 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
         {
             /* ---- phase 1: lane = path ---- */
             uint32_t q = q0 + lane;
-            uint32_t bin = 9;
+            uint32_t bin = 9, general = 0;
             if(q < total)
             {
                 uint32_t lp = p_begin, s = q;
-                if(L.pixels_per_task > 1) { lp += q / spp; s = q % spp; }
-                bin = trace_path<R>(g, ix, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
+                if(!paired) { lp += q / spp; s = q % spp; }
+                uint32_t r = trace_path<R>(g, ix, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
+                bin = r & 255u; general = r >> 8;
             }
             __syncwarp();
 #pragma unroll
@@ -1017,12 +1051,78 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                 uint32_t votes = __popc(__ballot_sync(0xffffffffu, bin == d));
                 if(lane == d) hist += votes;
             }
-            /* ---- phase 2: lane = wavelength, paths in sample order ---- */
+            /* ---- phase 2: half warp = path, lane16 = wavelength ---- */
             const uint32_t count = min((uint32_t)DRT_WARP, total - q0);
             const uint32_t my_nb = __float_as_uint(rec[REC_NB * DRT_WARP + lane]);
-            for(uint32_t slot = 0; slot < count; slot += 1)
+            if(paired)
             {
-                if(cur_s == spp)   /* next pixel of the task (only when a task holds several pixels, spp < 32) */
+                /* K5, warp scope: order the batch so that the two halves of the warp get paths of like cost.  Key = inactive
+                 * lanes last, paths without any bounce record first, then plastic-only paths by bounce count, then paths
+                 * that need the general shader by bounce count; a 32-wide bitonic sort over (key, lane).  The film is a
+                 * sum / Welford accumulation, so the order only changes rounding. */
+                uint32_t key = (lane >= count) ? 63u : (my_nb == 0u) ? 0u : min(my_nb, 15u) + (general ? 32u : 0u);
+                uint32_t v = (key << 5) | lane;
+#pragma unroll
+                for(uint32_t k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                    for(uint32_t j = k >> 1; j > 0; j >>= 1)
+                    {
+                        uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
+                        bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+                        v = keep_min ? min(v, other) : max(v, other);
+                    }
+                const uint32_t nzero = __popc(__ballot_sync(0xffffffffu, key == 0u));
+                if(half == 0)   /* paths that contributed nothing: count them, exact no-op on an unlit pixel */
+                {
+                    if(!film.lit) film.cnt += (float)nzero;
+                    else for(uint32_t i = 0; i < nzero; i += 1) film.add_zero();
+                }
+                if(L.path_dump || L.record_dump)
+                {
+                    for(uint32_t i = 0; i < nzero; i += 1)
+                    {
+                        uint32_t slot = __shfl_sync(0xffffffffu, v, i) & 31u;
+                        if(half == 0)
+                        {
+                            if(L.record_dump)
+                                for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
+                                    L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
+                            if(L.path_dump)
+                                for(uint32_t wl = lane16; wl < n; wl += DRT_HALF) L.path_dump[((size_t)cur_lp * spp + q0 + slot) * n + wl] = 0.f;
+                        }
+                    }
+                }
+                for(uint32_t i = nzero; i < count; i += 2)
+                {
+                    const uint32_t pos = i + half;
+                    const uint32_t slot = __shfl_sync(0xffffffffu, v, pos & 31u) & 31u;
+                    const uint32_t nb = __shfl_sync(0xffffffffu, my_nb, slot);
+                    if(pos < count)
+                    {
+                        float c[NS];
+                        replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, e0, c);
+                        film.add(c);
+                        if(L.record_dump)
+                            for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
+                                L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
+                        if(L.path_dump)
+                        {
+#pragma unroll
+                            for(int k = 0; k < NS; k += 1)
+                            {
+                                uint32_t wl = lane16 + k * DRT_HALF;
+                                if(wl < n) L.path_dump[((size_t)cur_lp * spp + q0 + slot) * n + wl] = c[k];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            /* several pixels per task (spp < 32): the lower half walks the slots in order and handles pixel boundaries */
+            for(uint32_t i = 0; i < count; i += 1)
+            {
+                if(cur_s == spp)
                 {
                     if(have_film) film_store<NS>(L.film, cur_y * L.width + cur_x, n, lane, film);
                     cur_lp += 1; cur_s = 0;
@@ -1031,35 +1131,39 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                     film.clear();
                     if(L.accumulate && have_film) film = film_load<NS>(L.film, cur_y * L.width + cur_x, n, lane);
                 }
-                const uint32_t nb = __shfl_sync(0xffffffffu, my_nb, slot);
-                float c[NS];
-                if(nb == 0)
+                const uint32_t nb = __shfl_sync(0xffffffffu, my_nb, i);
+                if(half == 0)
                 {
-#pragma unroll
-                    for(int k = 0; k < NS; k += 1) c[k] = 0.f;
-                    film.add_zero();
-                }
-                else
-                {
-                    replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, e0, c);
-                    film.add(c);
-                }
-                if(L.record_dump)
-                    for(uint32_t wd = lane; wd < L.path_words; wd += DRT_WARP)
-                        L.record_dump[((size_t)cur_lp * spp + cur_s) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
-                if(L.path_dump)
-                {
-#pragma unroll
-                    for(int k = 0; k < NS; k += 1)
+                    float c[NS];
+                    if(nb == 0)
                     {
-                        uint32_t wl = lane + k * DRT_WARP;
-                        if(wl < n) L.path_dump[((size_t)cur_lp * spp + cur_s) * n + wl] = c[k];
+#pragma unroll
+                        for(int k = 0; k < NS; k += 1) c[k] = 0.f;
+                        film.add_zero();
+                    }
+                    else
+                    {
+                        replay_path<NS>(rec + i, nb, g, ix, pool_lane, L, e0, c);
+                        film.add(c);
+                    }
+                    if(L.record_dump)
+                        for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
+                            L.record_dump[((size_t)cur_lp * spp + cur_s) * L.path_words + wd] = rec[wd * DRT_WARP + i];
+                    if(L.path_dump)
+                    {
+#pragma unroll
+                        for(int k = 0; k < NS; k += 1)
+                        {
+                            uint32_t wl = lane16 + k * DRT_HALF;
+                            if(wl < n) L.path_dump[((size_t)cur_lp * spp + cur_s) * n + wl] = c[k];
+                        }
                     }
                 }
                 cur_s += 1;
             }
             __syncwarp();
         }
+        if(paired) film.merge_halves();
         if(have_film) film_store<NS>(L.film, cur_y * L.width + cur_x, n, lane, film);
     }
 
@@ -1092,12 +1196,12 @@ static cudaError_t launch_render_ns(const RenderLaunch &L, int nslots, int grid,
         e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         if(e != cudaSuccess) return e; \
         drt::render_kernel<R, NS><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
-    switch(nslots)
+    switch(nslots)   /* wavelength slots per lane of a half warp: N <= 32, 48, 80, 128 */
     {
-        case 1: DRT_LAUNCH(1); break;
         case 2: DRT_LAUNCH(2); break;
         case 3: DRT_LAUNCH(3); break;
-        default: DRT_LAUNCH(4); break;
+        case 5: DRT_LAUNCH(5); break;
+        default: DRT_LAUNCH(8); break;
     }
 #undef DRT_LAUNCH
     return cudaGetLastError();

@@ -95,7 +95,8 @@ def test_film_matches_oracle(ctx):
 
 
 def test_sample_ranges_compose(ctx):
-    """Rendering [0,a) then accumulating [a,b) equals rendering [0,b) (same per-path streams, same Welford order)."""
+    """Rendering [0,a) then accumulating [a,b) equals rendering [0,b): same per-path streams; the partial films are merged in a
+    different order (pairwise update of count/mean/M2), so planes agree to rounding, the sample count exactly."""
     w, h, depth = 32, 32, 4
     cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, 48, depth)
     ctx.upload_scene(scene, camera, tables)
@@ -112,5 +113,7 @@ def test_sample_ranges_compose(ctx):
     ctx.render_device(oracledriver.params(w, h, 0, 20, depth, cfg.pixel_scheme, 5), cuda.film_from_tensors(*b))
     ctx.render_device(oracledriver.params(w, h, 20, 48, depth, cfg.pixel_scheme, 5), cuda.film_from_tensors(*b), accumulate=True)
     torch.cuda.synchronize()
-    for x, y in zip(a, b):
-        assert torch.equal(x, y)
+    assert torch.equal(a[1], b[1])
+    for x, y in zip((a[0], a[2], a[3]), (b[0], b[2], b[3])):
+        scale = float(x.abs().max())
+        assert float((x - y).abs().max()) <= 2e-5 * scale
