@@ -140,6 +140,10 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         }
         else if(f->type == DRT_GEO_SPHERE) pdf = (double)(4.0 * 3.1415926535897932385L * f->radius * f->radius);   /* :304 */
         g->light_pdf[i] = (R)pdf;
+        g->N4[i] = R4<R>{ g->nx[i], g->ny[i], g->nz[i], (R)f->type };
+        g->P4[i] = R4<R>{ g->px[i], g->py[i], g->pz[i], g->rad[i] };
+        g->U4[i] = R4<R>{ g->unx[i], g->uny[i], g->unz[i], g->ulen[i] };
+        g->V4[i] = R4<R>{ g->vnx[i], g->vny[i], g->vnz[i], g->vlen[i] };
         if(s->materials[f->material].is_emissive) g->light_surf[nl++] = i;
     }
     g->nlights = nl;

@@ -24,9 +24,16 @@
  * followed by the micro-normal cosine when BK_COND_MN is present. */
 enum { BK_CONST = 0, BK_DIFFUSE, BK_GLOSSY, BK_MIRROR, BK_DIEL_R, BK_COND_ON, BK_COND_MN, BK_COUNT };
 
+/* one surface as four 16-byte (f32) / 32-byte (f64) vectors, so that the intersection loop issues vector shared-memory loads */
+template <typename R> struct alignas(16) R4 { R x, y, z, w; };
+
 template <typename R>
 struct GeomT
 {
+    R4<R> N4[DRT_MAX_SURFACES];    /* plane normal | w = geometry type (DRT_GEO_*) as a number */
+    R4<R> P4[DRT_MAX_SURFACES];    /* position | w = sphere radius */
+    R4<R> U4[DRT_MAX_SURFACES];    /* normalised bounds vector u | w = |u| */
+    R4<R> V4[DRT_MAX_SURFACES];    /* normalised bounds vector v | w = |v| */
     int nsurf, nlights, base_mat, escape_mat, nmat, n, eval_words, pad1;
     R   trans_num, trans_den;      /* (630 - w0), (w1 - w0) of value_at_wl, spectrum.c:150-162 */
     int type[DRT_MAX_SURFACES], mat[DRT_MAX_SURFACES], light_surf[DRT_MAX_SURFACES];

@@ -169,18 +169,33 @@ __device__ __forceinline__ float hit_sphere(V3<float> o, V3<float> d, V3<float> 
     return (s0 <= s1) ? s0 : s1;
 }
 
-template <typename R> __device__ __forceinline__ R hit_plane(const GeomT<R> &g, int i, V3<R> o, V3<R> d)   /* geometry.c:157-182 */
+/* line_plane_intersection, geometry.c:157-182, on the packed surface (n, p, u^ | |u|, v^ | |v|).  The bounds frame that the
+ * reference recomputes on every call (:166-170) is precomputed by the host; bounds are inclusive (Q21). */
+__device__ __forceinline__ double hit_plane(V3<double> o, V3<double> d, R4<double> n4, R4<double> p4, R4<double> u4, R4<double> v4)
 {
-    V3<R> n = mk<R>(g.nx[i], g.ny[i], g.nz[i]);
-    V3<R> p = mk<R>(g.px[i], g.py[i], g.pz[i]);
-    R dn = dot(d, n);
-    if(dn == R(0)) return Num<R>::inf();
-    R l = dot(p - o, n) / dn;
-    V3<R> j = (o + d * l) - p;
-    R ju = dot(j, mk<R>(g.unx[i], g.uny[i], g.unz[i]));
-    R jv = dot(j, mk<R>(g.vnx[i], g.vny[i], g.vnz[i]));
-    bool inside = l >= R(0) && R(0) <= ju && ju <= g.ulen[i] && R(0) <= jv && jv <= g.vlen[i];   /* inclusive bounds, Q21 */
-    return inside ? l : Num<R>::inf();
+    V3<double> n = mk<double>(n4.x, n4.y, n4.z), p = mk<double>(p4.x, p4.y, p4.z);
+    double dn = dot(d, n);
+    if(dn == 0.0) return Num<double>::inf();
+    double l = dot(p - o, n) / dn;
+    V3<double> j = (o + d * l) - p;
+    double ju = dot(j, mk<double>(u4.x, u4.y, u4.z));
+    double jv = dot(j, mk<double>(v4.x, v4.y, v4.z));
+    bool inside = l >= 0.0 && 0.0 <= ju && ju <= u4.w && 0.0 <= jv && jv <= v4.w;
+    return inside ? l : Num<double>::inf();
+}
+/* f32: same test; the in-plane offset is formed as d*l - (p - o), which reuses p - o (3 instructions fewer, same value up
+ * to rounding) */
+__device__ __forceinline__ float hit_plane(V3<float> o, V3<float> d, R4<float> n4, R4<float> p4, R4<float> u4, R4<float> v4)
+{
+    V3<float> n = mk<float>(n4.x, n4.y, n4.z);
+    float dn = dot(d, n);
+    V3<float> po = mk<float>(p4.x - o.x, p4.y - o.y, p4.z - o.z);
+    float l = dot(po, n) / dn;
+    V3<float> j = mk<float>(fmaf(d.x, l, -po.x), fmaf(d.y, l, -po.y), fmaf(d.z, l, -po.z));
+    float ju = dot(j, mk<float>(u4.x, u4.y, u4.z));
+    float jv = dot(j, mk<float>(v4.x, v4.y, v4.z));
+    bool inside = dn != 0.f && l >= 0.f && 0.f <= ju && ju <= u4.w && 0.f <= jv && jv <= v4.w;
+    return inside ? l : Num<float>::inf();
 }
 
 /* Nearest surface strictly closer than `limit` along the ray, or -1 (the loops of find_ray_intersection
@@ -192,10 +207,11 @@ template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R>
     int found = -1;
     for(int i = 0; i < g.nsurf; i += 1)
     {
-        int t = g.type[i];
+        R4<R> n4 = g.N4[i], p4 = g.P4[i];
+        int t = (int)n4.w;
         R dist;
-        if(t == DRT_GEO_SPHERE) dist = hit_sphere(o, d, mk<R>(g.px[i], g.py[i], g.pz[i]), g.rad[i]);
-        else if(t == DRT_GEO_PLANE) dist = hit_plane<R>(g, i, o, d);
+        if(t == DRT_GEO_SPHERE) dist = hit_sphere(o, d, mk<R>(p4.x, p4.y, p4.z), p4.w);
+        else if(t == DRT_GEO_PLANE) dist = hit_plane(o, d, n4, p4, g.U4[i], g.V4[i]);
         else continue;
         if(dist < best) { best = dist; found = i; }
     }
