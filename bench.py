@@ -367,6 +367,13 @@ def run_b200_arm(a):
         except Exception:
             hbm_peak = 6650.0
         value = paths_per_step * a.steps / (ms_total * 1e-3)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+            if (a.width, a.height) == (1024, 1024):
+                traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_written_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": "camera_paths_per_sec", "value": value, "unit": "paths/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -383,8 +390,9 @@ def run_b200_arm(a):
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                         "kernel": "drt::render_kernel<float,3>", "kernel_ms": kernel_ms,
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (profiles/ncu_traffic.json); null for other image sizes",
+                         "kernel": "drt::render_kernel<float,5>" if a.geometry == "f32" else "drt::render_kernel<double,5>", "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_path": flops_path,
                          "peak_source": "measured in this run by drt_cuda_measure_fp32_peak (FFMA, 2 flops); MEASURED_PEAKS.json has no FP32 entry",
                          "hbm": {"achieved": film_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
