@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) film_merge_filter_kernel(float *dst, cons
  * (sum/filter, mean, M2/max) to packed BGRA.  One kernel replaces reduce-scatter + gather + three conversions. */
 struct FilmSet { int count; FilmPtrs film[16]; };
 
+template <int CHUNK>
 __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables *tables, FilmSet set, FilmPtrs dst, uint32_t pixel_begin,
                                                                 uint32_t pixel_end, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
 {
@@ -144,24 +145,40 @@ __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables 
         float cnt = 0.f, sum[DRT_MAX_SLOTS], mean[DRT_MAX_SLOTS], m2[DRT_MAX_SLOTS];
 #pragma unroll
         for(int k = 0; k < DRT_MAX_SLOTS; k += 1) { sum[k] = 0.f; mean[k] = 0.f; m2[k] = 0.f; }
-        for(int g = 0; g < set.count; g += 1)
+        /* ranks are taken CHUNK at a time: all their loads (peer memory over NVLink) are issued before any is consumed */
+        for(int g0 = 0; g0 < set.count; g0 += CHUNK)
         {
-            const FilmPtrs &f = set.film[g];
-            float nb = f.filter[p];
-            float nab = cnt + nb;
-            float wb = (nab > 0.f) ? nb / nab : 0.f;
+            float nb[CHUNK], rs[CHUNK][DRT_MAX_SLOTS], rm[CHUNK][DRT_MAX_SLOTS], rv[CHUNK][DRT_MAX_SLOTS];
 #pragma unroll
-            for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+            for(int c = 0; c < CHUNK; c += 1)
             {
-                uint32_t wl = lane + k * 32;
-                if(wl >= n) continue;
-                size_t at = (size_t)p * n + wl;
-                float mb = f.mean[at], delta = mb - mean[k];
-                m2[k] = m2[k] + f.m2[at] + delta * delta * cnt * wb;
-                mean[k] = fmaf(delta, wb, mean[k]);
-                sum[k] += f.sum[at];
+                const bool on = g0 + c < set.count;
+                const FilmPtrs &f = set.film[on ? g0 + c : g0];
+                nb[c] = on ? f.filter[p] : 0.f;
+#pragma unroll
+                for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+                {
+                    uint32_t wl = lane + k * 32;
+                    size_t at = (size_t)p * n + wl;
+                    bool ld = on && wl < n;
+                    rs[c][k] = ld ? f.sum[at] : 0.f; rm[c][k] = ld ? f.mean[at] : 0.f; rv[c][k] = ld ? f.m2[at] : 0.f;
+                }
             }
-            cnt = nab;
+#pragma unroll
+            for(int c = 0; c < CHUNK; c += 1)
+            {
+                float nab = cnt + nb[c];
+                float wb = (nab > 0.f) ? nb[c] / nab : 0.f;
+#pragma unroll
+                for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
+                {
+                    float delta = rm[c][k] - mean[k];
+                    m2[k] = m2[k] + rv[c][k] + delta * delta * cnt * wb;
+                    mean[k] = fmaf(delta, wb, mean[k]);
+                    sum[k] += rs[c][k];
+                }
+                cnt = nab;
+            }
         }
         float peak = 0.f;
 #pragma unroll
@@ -277,8 +294,12 @@ void drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs 
     drt::FilmSet set;
     set.count = count;
     for(int i = 0; i < count && i < 16; i += 1) set.film[i] = films[i];
-    drt::film_gather_merge_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
-                                                           bgra_sum, bgra_mean, bgra_var);
+    if(count <= 2)
+        drt::film_gather_merge_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
+                                                                  bgra_sum, bgra_mean, bgra_var);
+    else
+        drt::film_gather_merge_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
+                                                                  bgra_sum, bgra_mean, bgra_var);
 }
 
 size_t drt_rgb_tables_bytes(void) { return sizeof(drt::RgbTables); }
