@@ -140,13 +140,24 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         }
         else if(f->type == DRT_GEO_SPHERE) pdf = (double)(4.0 * 3.1415926535897932385L * f->radius * f->radius);   /* :304 */
         g->light_pdf[i] = (R)pdf;
-        g->N4[i] = R4<R>{ g->nx[i], g->ny[i], g->nz[i], (R)f->type };
-        g->P4[i] = R4<R>{ g->px[i], g->py[i], g->pz[i], g->rad[i] };
-        g->U4[i] = R4<R>{ g->unx[i], g->uny[i], g->unz[i], g->ulen[i] };
-        g->V4[i] = R4<R>{ g->vnx[i], g->vny[i], g->vnz[i], g->vlen[i] };
         if(s->materials[f->material].is_emissive) g->light_surf[nl++] = i;
     }
     g->nlights = nl;
+    /* packed copies regrouped by type for the intersection loops */
+    int slot = 0;
+    for(int pass = 0; pass < 2; pass += 1)
+        for(int i = 0; i < s->num_surfaces; i += 1)
+        {
+            int want = pass == 0 ? DRT_GEO_PLANE : DRT_GEO_SPHERE;
+            if(s->surfaces[i].type != want) continue;
+            g->sid[slot] = i;
+            g->N4[slot] = R4<R>{ g->nx[i], g->ny[i], g->nz[i], (R)0 };
+            g->P4[slot] = R4<R>{ g->px[i], g->py[i], g->pz[i], g->rad[i] };
+            g->U4[slot] = R4<R>{ g->unx[i], g->uny[i], g->unz[i], g->ulen[i] };
+            g->V4[slot] = R4<R>{ g->vnx[i], g->vny[i], g->vnz[i], g->vlen[i] };
+            slot += 1;
+            if(pass == 0) g->nplanes += 1; else g->nspheres += 1;
+        }
     for(int m = 0; m < s->num_materials; m += 1)
     {
         const drt_material *mm = &s->materials[m];

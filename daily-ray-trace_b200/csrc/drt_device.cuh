@@ -30,7 +30,11 @@ template <typename R> struct alignas(16) R4 { R x, y, z, w; };
 template <typename R>
 struct GeomT
 {
-    R4<R> N4[DRT_MAX_SURFACES];    /* plane normal | w = geometry type (DRT_GEO_*) as a number */
+    /* intersectable surfaces regrouped by type: slots [0, nplanes) are planes, [nplanes, nplanes + nspheres) spheres;
+     * sid[slot] is the surface's index in the scene (ties in distance go to the lower scene index, Q21) */
+    int   nplanes, nspheres, pad2, pad3;
+    int   sid[DRT_MAX_SURFACES];
+    R4<R> N4[DRT_MAX_SURFACES];    /* plane normal | w unused */
     R4<R> P4[DRT_MAX_SURFACES];    /* position | w = sphere radius */
     R4<R> U4[DRT_MAX_SURFACES];    /* normalised bounds vector u | w = |u| */
     R4<R> V4[DRT_MAX_SURFACES];    /* normalised bounds vector v | w = |v| */

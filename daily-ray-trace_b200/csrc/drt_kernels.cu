@@ -204,19 +204,27 @@ __device__ __forceinline__ float hit_plane(V3<float> o, V3<float> d, R4<float> n
 template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, R *dist_out)
 {
     R best = limit;
-    int found = -1;
-    for(int i = 0; i < g.nsurf; i += 1)
+    int found = 1 << 30;   /* scene index of the nearest surface so far */
+    /* planes, then spheres: no type switch inside the loops.  A candidate replaces the current one when it is strictly
+     * nearer, or equally near with a lower scene index -- the result of the reference's single in-order loop. */
+    const int np = g.nplanes, ns = g.nspheres;
+#pragma unroll 1
+    for(int k = 0; k < np; k += 1)
     {
-        R4<R> n4 = g.N4[i], p4 = g.P4[i];
-        int t = (int)n4.w;
-        R dist;
-        if(t == DRT_GEO_SPHERE) dist = hit_sphere(o, d, mk<R>(p4.x, p4.y, p4.z), p4.w);
-        else if(t == DRT_GEO_PLANE) dist = hit_plane(o, d, n4, p4, g.U4[i], g.V4[i]);
-        else continue;
-        if(dist < best) { best = dist; found = i; }
+        R dist = hit_plane(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k]);
+        int id = g.sid[k];
+        if(dist < best || (dist == best && dist < limit && id < found)) { best = dist; found = id; }
+    }
+#pragma unroll 1
+    for(int k = np; k < np + ns; k += 1)
+    {
+        R4<R> p4 = g.P4[k];
+        R dist = hit_sphere(o, d, mk<R>(p4.x, p4.y, p4.z), p4.w);
+        int id = g.sid[k];
+        if(dist < best || (dist == best && dist < limit && id < found)) { best = dist; found = id; }
     }
     *dist_out = best;
-    return found;
+    return (found == (1 << 30)) ? -1 : found;
 }
 
 template <typename R> struct Hit
