@@ -15,7 +15,7 @@
 #include "drt_cuda.h"
 #include "drt_device.cuh"
 
-cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
 size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps);
 void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
@@ -47,6 +47,7 @@ struct drt_cuda_context
     bool   have_scene = false;
     bool   f64_geometry = false;
     int    n = 0, nslots = 0, nlights = 0, eval_words = 1;
+    bool   all_fast = false;      /* every surface material has a plastic block (SpdIndex::plastic): the specialised kernel applies */
     void  *d_geom32 = nullptr, *d_geom64 = nullptr;
     SpdIndex *d_index = nullptr;
     float *d_pool = nullptr;
@@ -238,6 +239,47 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
             for(int i = 0; i < n; i += 1) pool[at + (size_t)i] = (float)scene->materials[m].spd[k][i];
         }
     index.nrows = rows;
+    /* interleaved plastic blocks (SpdIndex::plastic) for the two-lobe Blinn-Phong materials when the scene has one light */
+    if(g32->nlights == 1)
+    {
+        const double *emission = scene->materials[scene->surfaces[g32->light_surf[0]].material].spd[DRT_SPD_EMISSION];
+        const bool have_e = (scene->materials[scene->surfaces[g32->light_surf[0]].material].spd_mask & (1 << DRT_SPD_EMISSION)) != 0;
+        for(int m = 0; m < scene->num_materials; m += 1)
+        {
+            const drt_material *mm = &scene->materials[m];
+            if(mm->is_black_body || mm->num_lobes != 2 || g32->bmask[m] != ((1 << BK_DIFFUSE) | (1 << BK_GLOSSY))) continue;
+            size_t at = (pool.size() + 3) & ~(size_t)3;
+            pool.resize(at + (size_t)half_slots * 64, 0.f);
+            index.plastic[m] = (int)at;
+            auto val = [&](int k, int slot, int lane) -> float {
+                int wl = lane + slot * 16;
+                return (wl < n && (mm->spd_mask & (1 << k))) ? (float)mm->spd[k][wl] : 0.f;
+            };
+            auto emi = [&](int slot, int lane) -> float {
+                int wl = lane + slot * 16;
+                return (wl < n && have_e) ? (float)emission[wl] : 0.f;
+            };
+            const int np = half_slots / 2;
+            for(int lane = 0; lane < 16; lane += 1)
+            {
+                for(int pr = 0; pr < np; pr += 1)
+                    for(int j = 0; j < 2; j += 1)
+                    {
+                        int slot = 2 * pr + j;
+                        float d = val(DRT_SPD_DIFFUSE, slot, lane), gl = val(DRT_SPD_GLOSSY, slot, lane), e = emi(slot, lane);
+                        float *c0 = &pool[at + ((size_t)(2 * pr) * 16 + lane) * 4], *c1 = &pool[at + ((size_t)(2 * pr + 1) * 16 + lane) * 4];
+                        c0[j] = d; c0[2 + j] = gl; c1[j] = d * e; c1[2 + j] = gl * e;
+                    }
+                if(half_slots & 1)
+                {
+                    int slot = half_slots - 1;
+                    float d = val(DRT_SPD_DIFFUSE, slot, lane), gl = val(DRT_SPD_GLOSSY, slot, lane), e = emi(slot, lane);
+                    float *c = &pool[at + ((size_t)(half_slots - 1) * 16 + lane) * 4];
+                    c[0] = d; c[1] = gl; c[2] = d * e; c[3] = gl * e;
+                }
+            }
+        }
+    }
 
     std::vector<unsigned char> rgbt(drt_rgb_tables_bytes());
     drt_fill_rgb_tables(rgbt.data(), tables);
@@ -257,10 +299,16 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_rgb_tables, rgbt.data(), rgbt.size(), cudaMemcpyHostToDevice);
     int nlights = g32->nlights;
+    bool all_fast = nlights == 1;
+    for(int i = 0; i < scene->num_surfaces; i += 1)
+    {
+        const drt_material *mm = &scene->materials[scene->surfaces[i].material];
+        if(!mm->is_black_body && index.plastic[scene->surfaces[i].material] == 0) all_fast = false;
+    }
     int eval_words = g32->eval_words > 0 ? g32->eval_words : 1;
     delete g32; delete g64;
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "scene upload: %s", cudaGetErrorString(e));
-    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->eval_words = eval_words; ctx->pool_words = (uint32_t)pool.size();
+    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->eval_words = eval_words; ctx->all_fast = all_fast; ctx->pool_words = (uint32_t)pool.size();
     ctx->upload_bytes = sizeof(GeomT<float>) + sizeof(GeomT<double>) + sizeof(SpdIndex) + pool.size() * 4 + rgbt.size();
     ctx->have_scene = true;
     return DRT_CUDA_OK;
@@ -307,8 +355,10 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     uint32_t spp = p->sample_end - p->sample_begin;
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
     L.eval_words = (uint32_t)ctx->eval_words;
-    L.bounce_words = 2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words;
-    L.path_words = 2 + p->max_depth * L.bounce_words;
+    L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
+    if(L.bounce_words < 8) L.bounce_words = 8;
+    L.path_words = 4 + p->max_depth * L.bounce_words;
+    L.path_stride = ((L.path_words / 4) & 1u) ? L.path_words : L.path_words + 4;
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
     int warps = DRT_CTA_WARPS;
@@ -331,7 +381,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     if(grid > need) grid = need;
     CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), stream));
-    cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->nslots, (int)grid, warps, smem, stream);
+    cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->all_fast, ctx->nslots, (int)grid, warps, smem, stream);
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
     ctx->last_launches = 1;

@@ -66,6 +66,13 @@ struct SpdIndex
 {
     int n, nslots, npad, nrows;
     int row[DRT_MAX_MATERIALS][DRT_SPD_COUNT];
+    /* word offset (multiple of 4) of the material's interleaved "plastic block", 0 if it has none: the diffuse and glossy
+     * rows D, G and their products DE, GE with the emission of light 0, laid out so that a half-warp lane fetches all it
+     * needs for one bounce with 16-byte loads that land in f32x2 register pairs.  For wavelength slots (2p, 2p+1) of lane l:
+     *   chunk 2p   = { D[2p], D[2p+1], G[2p], G[2p+1] }      chunk 2p+1 = { DE[2p], DE[2p+1], GE[2p], GE[2p+1] }
+     * and for an odd last slot s the last chunk (index nslots - 1) = { D[s], G[s], DE[s], GE[s] }; chunk c of lane l is the
+     * float4 at index c*16 + l of the block (nslots*64 words in all). */
+    int plastic[DRT_MAX_MATERIALS];
 };
 
 struct FilmPtrs { float *sum, *filter, *mean, *m2; };
@@ -77,13 +84,20 @@ struct DeviceStats
     unsigned long long reached_depth_cap;
 };
 
-/* Path record in shared memory, one column per path slot (word w of slot s at rec[w*32 + s]):
+/* Path record in shared memory, one row per path slot (word w of slot s at rec[s*path_stride + w]; path_stride is 4 times an
+ * odd number, so the 16-byte stores of 32 lanes and the scalar stores of 8 consecutive lanes are bank-conflict free):
  *   word 0            number of bounce records
  *   word 1            vignette factor
- *   per bounce        [0] header: kind(2) | surface material(5) | media swapped(1) | light visibility mask(16)
- *                     [1] on_dot
- *                     nlights x { eval weights (eval_words), light scale k }      next-event estimation
- *                     eval weights (eval_words)                                   sampled direction, x 1/pdf    */
+ *   words 2, 3        unused (bounces start 16-byte aligned)
+ *   per bounce, general   [0] header: kind(2) | 0<<2 | surface material(5)<<3 | media swapped<<8 | light visibility mask(16)<<16
+ *                         [1] on_dot
+ *                         nlights x { eval weights (eval_words), light scale k }      next-event estimation
+ *                         eval weights (eval_words)                                   sampled direction, x 1/pdf
+ *   per bounce, fast      two-lobe plastic under the scene's only light:
+ *                         [0] header: kind(2) | 1<<2 | plastic block float4 index<<4
+ *                         [1] w_diffuse * k  [2] w_glossy * k   (next-event estimation, 0 when the light is hidden)
+ *                         [4] w_diffuse / pdf [5] w_glossy / pdf (sampled direction)
+ *   bounce_words is a multiple of 4 and at least 8. */
 struct RenderLaunch
 {
     const void     *geom;          /* GeomT<float> or GeomT<double> in global memory */
@@ -105,6 +119,7 @@ struct RenderLaunch
     uint32_t pixels_per_task;      /* contiguous rectangle pixels claimed per warp task */
     uint32_t eval_words;           /* stored weights per BSDF evaluation (scene-wide maximum) */
     uint32_t bounce_words;         /* 2 + nlights*(eval_words+1) + eval_words */
-    uint32_t path_words;           /* 2 + max_depth*bounce_words */
+    uint32_t path_words;           /* 4 + max_depth*bounce_words */
+    uint32_t path_stride;          /* words between the records of consecutive slots: >= path_words, 4 * odd */
     uint32_t geom_bytes, pool_words;
 };

@@ -278,7 +278,7 @@ template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g,
  * lobes that "do not write" leave the previous lobe's value in it (Q7).  Every lobe output is a scalar times one of
  * seven spectra: 1, diffuse, glossy, mirror, R_dielectric(on_dot), F_conductor(on_dot), F_conductor(mn_dot).  Walking
  * the lobe list with a 7-vector as the scratch reproduces the sum, stale values included, as 7 weights.  The weights
- * the material can produce (g.bmask) are stored to the record column `rec` (already offset to the slot) from word `at`. */
+ * the material can produce (g.bmask) are stored to the path record `rec` (already offset to the slot) from word `at`. */
 #define BMASK_PLASTIC ((1 << BK_DIFFUSE) | (1 << BK_GLOSSY))
 
 template <typename R>
@@ -359,29 +359,22 @@ __device__ __noinline__ void eval_weights_general(const GeomT<R> &g, int m, V3<R
     const int mask = g.bmask[m];
 #pragma unroll
     for(int k = 0; k < BK_COUNT; k += 1)
-        if(mask & (1 << k)) { rec[at * DRT_WARP] = acc[k] * scale; at += 1; }
-    if(mask & (1 << BK_COND_MN)) rec[at * DRT_WARP] = mn_cos;
+        if(mask & (1 << k)) { rec[at] = acc[k] * scale; at += 1; }
+    if(mask & (1 << BK_COND_MN)) rec[at] = mn_cos;
 }
 
-/* Hot case inline: the two-lobe Blinn-Phong plastic (bp_diffuse_bdsf, bp_glossy_bdsf) of every shipped wall and ball
- * needs two weights and no lobe walk; every other lobe list goes through the out-of-line general evaluator. */
+/* Hot case inline: the two-lobe Blinn-Phong plastic (bp_diffuse_bdsf, bp_glossy_bdsf, bdsf.c:105-119) of every shipped wall
+ * and ball needs two weights and no lobe walk; every other lobe list goes through the out-of-line general evaluator. */
 template <typename R>
-__device__ __forceinline__ void eval_weights(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in, int match, float scale,
-                                             float *rec, uint32_t at)
+__device__ __forceinline__ void plastic_weights(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, V3<R> in, float scale, float &wd, float &wg)
 {
-    if(g.bmask[m] == BMASK_PLASTIC && g.nlobes[m] == 2)
-    {
-        R cos_in = r_abs(dot(nrm, in));
-        V3<R> bis = normalise(out + in);
-        R nb = dot(nrm, bis);
-        R coef = r_pow((R(0) > nb) ? R(0) : nb, g.shin[m]);
-        rec[at * DRT_WARP] = (float)((R(1) / Num<R>::pi()) * cos_in) * scale;
-        rec[(at + 1) * DRT_WARP] = (float)(coef * cos_in) * scale;
-        return;
-    }
-    eval_weights_general<R>(g, m, nrm, out, on_dot, in, match, scale, rec, at);
+    R cos_in = r_abs(dot(nrm, in));
+    V3<R> bis = normalise(out + in);
+    R nb = dot(nrm, bis);
+    R coef = r_pow((R(0) > nb) ? R(0) : nb, g.shin[m]);
+    wd = (float)((R(1) / Num<R>::pi()) * cos_in) * scale;
+    wg = (float)(coef * cos_in) * scale;
 }
-
 /* dielectric Fresnel at one wavelength, bdsf.c:44-66 (Q9 kept) */
 template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr, T inc_cos)
 {
@@ -564,19 +557,19 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 #endif
 #define REC_NB   0
 #define REC_VIG  1
-#define REC_HEAD 2
+#define REC_HEAD 4
 #define KIND_SHADE 1u
 #define KIND_EMIT  2u
-/* bounce header word:
- *   fast (two-lobe plastic, one light):  kind(2) | 1<<2 | light visible<<3 | diffuse row offset(14)<<4 | glossy row offset(14)<<18
+/* bounce header word (record layout: RenderLaunch in drt_device.cuh):
+ *   fast (two-lobe plastic, one light):  kind(2) | 1<<2 | plastic block float4 index<<4
  *   general:                             kind(2) | 0<<2 | surface material(5)<<3 | media swapped<<8 | light visibility mask(16)<<16
- * so the hot replay needs ONE header read and no material-table lookups. */
+ * so the hot replay needs two 16-byte record reads per bounce and no material-table lookups. */
 #define HDR_FAST 4u
 
 /* ------------------------------------------------------------------ phase 1: trace one path, emit its record
- * `rec` points at this lane's column (word w at rec[w*32]).  Returns the termination-histogram bin and a class bit. */
+ * `rec` points at this lane's record (16-byte aligned).  Returns the termination-histogram bin and a class bit. */
 
-template <typename R>
+template <typename R, bool ALLFAST>
 __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec,
                                                uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
 {
@@ -611,7 +604,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         o = point;
         d = normalise(ap - o);   /* Q1 */
     }
-    rec[REC_VIG * DRT_WARP] = (float)dot(d, fwd);   /* Q20 */
+    rec[REC_VIG] = (float)dot(d, fwd);   /* Q20 */
 
     uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth, general = 0;
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
@@ -627,16 +620,24 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         {
             if(flags & 2)
             {
-                rec[base * DRT_WARP] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
+                rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
                 nb += 1;
             }
             end_depth = depth;
             break;
         }
         shaded += 1;
+        /* two-lobe plastic: two weights per evaluation, computed inline; under a single light the bounce also has the fixed
+         * 8-word "fast" record.  Shadow rays, direction sampling and the weight arithmetic are shared by all materials so
+         * that a warp whose lanes sit on different materials does not run them twice. */
+        const int sm = h.surf_mat;
+        const bool plastic = ALLFAST || (g.bmask[sm] == BMASK_PLASTIC && g.nlobes[sm] == 2);
+        const bool fast = ALLFAST || (plastic && ix.plastic[sm] != 0);
+        const int nlights = ALLFAST ? 1 : g.nlights;
         /* K3: direct_light_contribution, :272-332 -- every emissive surface in index order; draws come before visibility */
         uint32_t vis_mask = 0;
-        for(int j = 0; j < g.nlights; j += 1)
+        float wd_n = 0.f, wg_n = 0.f;
+        for(int j = 0; j < nlights; j += 1)
         {
             int ls = g.light_surf[j];
             int lt = g.type[ls];
@@ -668,29 +669,44 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
             shadow += 1;
             if(visible<R>(g, h.pos, lp))
             {
-                uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
-                eval_weights<R>(g, h.surf_mat, h.nrm, h.out, h.on_dot, normalise(lp - h.pos), 0, 1.f, rec, e);
-                rec[(e + ew) * DRT_WARP] = (float)k;
+                const uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+                const V3<R> ldir = normalise(lp - h.pos);
+                if(plastic)
+                {
+                    plastic_weights<R>(g, sm, h.nrm, h.out, ldir, fast ? (float)k : 1.f, wd_n, wg_n);
+                    if(!fast) { rec[e] = wd_n; rec[e + 1] = wg_n; }
+                }
+                else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, 1.f, rec, e);
+                if(!fast) rec[e + ew] = (float)k;
                 vis_mask |= 1u << j;
             }
         }
         /* K4: sample the next direction and evaluate the BSDF for it, cast_ray :464-472 */
         V3<R> in; R inv_pdf; int match;
         sample_direction<R>(g, h, rng, in, inv_pdf, match);
-        eval_weights<R>(g, h.surf_mat, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, base + 2 + (ew + 1) * (uint32_t)g.nlights);
-        uint32_t swapped = (h.inc_mat != g.base_mat) ? 1u : 0u;
-        uint32_t hdr = KIND_SHADE | ((uint32_t)h.surf_mat << 3) | (swapped << 8) | (vis_mask << 16);
-        if(g.bmask[h.surf_mat] == BMASK_PLASTIC && g.nlobes[h.surf_mat] == 2 && g.nlights == 1)
-            hdr = KIND_SHADE | HDR_FAST | ((vis_mask & 1u) << 3) | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_DIFFUSE] << 4)
-                  | ((uint32_t)ix.row[h.surf_mat][DRT_SPD_GLOSSY] << 18);
-        else general = 1;
-        rec[base * DRT_WARP] = __uint_as_float(hdr);
-        rec[(base + 1) * DRT_WARP] = (float)h.on_dot;
+        const uint32_t es = base + 2 + (ew + 1) * (uint32_t)nlights;
+        float wd_s = 0.f, wg_s = 0.f;
+        if(plastic) plastic_weights<R>(g, sm, h.nrm, h.out, in, (float)inv_pdf, wd_s, wg_s);
+        else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, es);
+        if(fast)
+        {
+            float4 *r4 = reinterpret_cast<float4 *>(rec + base);
+            r4[0] = make_float4(__uint_as_float(KIND_SHADE | HDR_FAST | ((uint32_t)ix.plastic[sm] << 2)), wd_n, wg_n, 0.f);
+            r4[1] = make_float4(wd_s, wg_s, 0.f, 0.f);
+        }
+        else
+        {
+            general = 1;
+            if(plastic) { rec[es] = wd_s; rec[es + 1] = wg_s; }
+            uint32_t swapped = (h.inc_mat != g.base_mat) ? 1u : 0u;
+            rec[base] = __uint_as_float(KIND_SHADE | ((uint32_t)sm << 3) | (swapped << 8) | (vis_mask << 16));
+            rec[base + 1] = (float)h.on_dot;
+        }
         nb += 1;
         d = in;
         o = h.pos;
     }
-    rec[REC_NB * DRT_WARP] = __uint_as_float(nb);
+    rec[REC_NB] = __uint_as_float(nb);
     tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
     /* bits 0-7: histogram bin (depth of termination, 8 = hit the cap); bit 8: the record has a bounce that needs the general shader */
     return ((end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8) | (general << 8);
@@ -707,6 +723,9 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
 { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+/* MUFU.RCP alone (<= 1 ulp): the sample count of the Welford update is a small positive integer */
+__device__ __forceinline__ float r_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 /* o = a*b + c,  o = s*b + c,  o = a*b,  o = s*b  over NS wavelength slots */
 template <int NS> __device__ __forceinline__ void v_fma(float (&o)[NS], const float (&a)[NS], const float (&b)[NS], const float (&c)[NS])
@@ -786,13 +805,13 @@ __device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint
     EvalWeights e;
     e.w_const = e.w_d = e.w_g = e.w_m = e.w_r = e.w_a = e.c_a = e.w_b = e.c_b = 0.f;
     e.on_dot = on_dot;
-    if(mask & (1 << BK_CONST))   { e.w_const = col[at * DRT_WARP]; at += 1; }
-    if(mask & (1 << BK_DIFFUSE)) { e.w_d = col[at * DRT_WARP]; at += 1; }
-    if(mask & (1 << BK_GLOSSY))  { e.w_g = col[at * DRT_WARP]; at += 1; }
-    if(mask & (1 << BK_MIRROR))  { e.w_m = col[at * DRT_WARP]; at += 1; }
-    if(mask & (1 << BK_DIEL_R))  { e.w_r = col[at * DRT_WARP]; at += 1; }
-    if(mask & (1 << BK_COND_ON)) { e.w_a = col[at * DRT_WARP]; e.c_a = on_dot; at += 1; }
-    if(mask & (1 << BK_COND_MN)) { e.w_b = col[at * DRT_WARP]; e.c_b = col[(at + 1) * DRT_WARP]; }
+    if(mask & (1 << BK_CONST))   { e.w_const = col[at]; at += 1; }
+    if(mask & (1 << BK_DIFFUSE)) { e.w_d = col[at]; at += 1; }
+    if(mask & (1 << BK_GLOSSY))  { e.w_g = col[at]; at += 1; }
+    if(mask & (1 << BK_MIRROR))  { e.w_m = col[at]; at += 1; }
+    if(mask & (1 << BK_DIEL_R))  { e.w_r = col[at]; at += 1; }
+    if(mask & (1 << BK_COND_ON)) { e.w_a = col[at]; e.c_a = on_dot; at += 1; }
+    if(mask & (1 << BK_COND_MN)) { e.w_b = col[at]; e.c_b = col[at + 1]; }
     const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];     /* absent spectra point at the all-zero row */
     const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
     const float *mr = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
@@ -816,7 +835,7 @@ __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, ui
     const bool swapped = (hdr >> 8) & 1u;
     const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
     const uint32_t vis = hdr >> 16;
-    const float on_dot = col[(base + 1) * DRT_WARP];
+    const float on_dot = col[base + 1];
     float contrib[NS];
 #pragma unroll
     for(int k = 0; k < NS; k += 1) contrib[k] = 0.f;
@@ -826,7 +845,7 @@ __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, ui
         if(!((vis >> j) & 1u)) continue;
         uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
         Spec<NS> f = eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot);
-        float kk = col[(e + ew) * DRT_WARP];
+        float kk = col[e + ew];
         const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
 #pragma unroll
         for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_HALF]) * kk;   /* Q4 */
@@ -839,60 +858,78 @@ __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, ui
     return st;
 }
 
-/* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from record column `col` (nb >= 1 bounces);
+/* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from the record `col` (nb >= 1 bounces);
  * returns the path contribution already multiplied by the vignette factor (:612-615).
- * `e0` = emission of light 0 in registers (the only light of every shipped scene). */
-template <int NS, typename G>
-__device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool_lane,
-                                            const RenderLaunch &L, const float (&e0)[NS], float (&c)[NS])
+ * Throughput and radiance are held as f32x2 register pairs for wavelength slots (0,1), (2,3), ... plus one scalar for an
+ * odd last slot.  The hot bounce (two-lobe plastic under the scene's only light) is
+ *     radiance   += throughput * (wd_n k * DE + wg_n k * GE)        (NEE: bdsf * emission * k, :322-327; weights are 0 when shadowed)
+ *     throughput *= wd_s/pdf * D + wg_s/pdf * G                      (:467-469)
+ * with D, G, DE = D*E, GE = G*E fetched from the material's interleaved plastic block by 16-byte loads. */
+template <int NS, bool ALLFAST, typename G>
+__device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool, const float *pool_lane,
+                                            uint32_t lane16, const RenderLaunch &L, float (&c)[NS])
 {
-    ShadeState<NS> st;
+    constexpr int NP = NS / 2;
+    unsigned long long thr2[NP > 0 ? NP : 1], dst2[NP > 0 ? NP : 1];
+    float thr1 = 1.f, dst1 = 0.f;
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) { st.thr.v[k] = 1.f; st.dst.v[k] = 0.f; }
+    for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(1.f, 1.f); dst2[k] = pk2(0.f, 0.f); }
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
-    const float *p = col + REC_HEAD * DRT_WARP;
+    const float *p = col + REC_HEAD;
     uint32_t base = REC_HEAD;
-    uint32_t hdr_next = __float_as_uint(p[0]);
-    for(uint32_t b = 0; b < nb; b += 1, p += bw * DRT_WARP, base += bw)
+    float4 a_next = *reinterpret_cast<const float4 *>(p);
+    for(uint32_t b = 0; b < nb; b += 1, p += bw, base += bw)
     {
-        const uint32_t hdr = hdr_next;
-        if(b + 1 < nb) hdr_next = __float_as_uint(p[bw * DRT_WARP]);   /* next header in flight while this bounce is shaded */
-        if(hdr & HDR_FAST)
+        const float4 a = a_next;
+        if(b + 1 < nb) a_next = *reinterpret_cast<const float4 *>(p + bw);   /* next header in flight while this bounce is shaded */
+        const uint32_t hdr = __float_as_uint(a.x);
+        if(ALLFAST ? ((hdr & 3u) == KIND_SHADE) : ((hdr & HDR_FAST) != 0u))
         {
-            /* hot case: two-lobe plastic under one light.  Words: [2] wD [3] wG [2+ew] k (NEE), [3+ew] wD [4+ew] wG (sample) */
-            const float *dr = pool_lane + ((hdr >> 4) & 0x3fffu);
-            const float *gr = pool_lane + (hdr >> 18);
-            float d_row[NS], g_row[NS];
+            const float4 s4 = *reinterpret_cast<const float4 *>(p + 4);
+            const float4 *blk = reinterpret_cast<const float4 *>(pool) + (hdr >> 4) + lane16;
+            const unsigned long long wdn = pk2(a.y, a.y), wgn = pk2(a.z, a.z), wds = pk2(s4.x, s4.x), wgs = pk2(s4.y, s4.y);
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) { d_row[k] = dr[k * DRT_HALF]; g_row[k] = gr[k * DRT_HALF]; }
-            const float wd_n = p[2 * DRT_WARP], wg_n = p[3 * DRT_WARP], kk = p[(2 + ew) * DRT_WARP];
-            const float wd_s = p[(3 + ew) * DRT_WARP], wg_s = p[(4 + ew) * DRT_WARP];
-            float f[NS], t[NS];
-            if(hdr & 8u)   /* the light is visible */
+            for(int k = 0; k < NP; k += 1)
             {
-                v_mul_s<NS>(t, wd_n, d_row);
-                v_fma_s<NS>(f, wg_n, g_row, t);          /* f = wd*D + wg*G */
-                v_mul<NS>(f, f, e0);
-                v_mul_s<NS>(f, kk, f);                   /* (f * E) * k */
-                v_fma<NS>(st.dst.v, st.thr.v, f, st.dst.v);
+                const float4 dg = blk[(2 * k) * DRT_HALF], ee = blk[(2 * k + 1) * DRT_HALF];
+                unsigned long long f = fma2(wgn, pk2(ee.z, ee.w), mul2(wdn, pk2(ee.x, ee.y)));
+                dst2[k] = fma2(thr2[k], f, dst2[k]);
+                unsigned long long t = fma2(wgs, pk2(dg.z, dg.w), mul2(wds, pk2(dg.x, dg.y)));
+                thr2[k] = mul2(thr2[k], t);
             }
-            v_mul_s<NS>(t, wd_s, d_row);
-            v_fma_s<NS>(f, wg_s, g_row, t);
-            v_mul<NS>(st.thr.v, st.thr.v, f);
+            if(NS & 1)
+            {
+                const float4 q = blk[(NS - 1) * DRT_HALF];   /* D, G, DE, GE of the last slot */
+                dst1 = fmaf(thr1, fmaf(a.z, q.w, a.y * q.z), dst1);
+                thr1 *= fmaf(s4.y, q.y, s4.x * q.x);
+            }
             continue;
         }
-        if((hdr & 3u) == KIND_EMIT)
+        if(ALLFAST || (hdr & 3u) == KIND_EMIT)   /* the path ran into an emitter, cast_ray :453-457 */
         {
             const float *row = pool_lane + ix.row[(hdr >> 3) & 31][DRT_SPD_EMISSION];
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], row[k * DRT_HALF], st.dst.v[k]);
+            for(int k = 0; k < NP; k += 1) dst2[k] = fma2(thr2[k], pk2(row[(2 * k) * DRT_HALF], row[(2 * k + 1) * DRT_HALF]), dst2[k]);
+            if(NS & 1) dst1 = fmaf(thr1, row[(NS - 1) * DRT_HALF], dst1);
             break;
         }
-        st = shade_bounce_general<NS, G>(col, base, hdr, g, ix, pool_lane, ew, L.nlights, st);
-    }
-    const float vig = col[REC_VIG * DRT_WARP];
+        if constexpr(!ALLFAST)
+        {
+            ShadeState<NS> st;
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) c[k] = st.dst.v[k] * vig;
+            for(int k = 0; k < NP; k += 1) { upk2(thr2[k], st.thr.v[2 * k], st.thr.v[2 * k + 1]); upk2(dst2[k], st.dst.v[2 * k], st.dst.v[2 * k + 1]); }
+            if(NS & 1) { st.thr.v[NS - 1] = thr1; st.dst.v[NS - 1] = dst1; }
+            st = shade_bounce_general<NS, G>(col, base, hdr, g, ix, pool_lane, ew, L.nlights, st);
+#pragma unroll
+            for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(st.thr.v[2 * k], st.thr.v[2 * k + 1]); dst2[k] = pk2(st.dst.v[2 * k], st.dst.v[2 * k + 1]); }
+            if(NS & 1) { thr1 = st.thr.v[NS - 1]; dst1 = st.dst.v[NS - 1]; }
+        }
+    }
+    const float vig = col[REC_VIG];
+    const unsigned long long vig2 = pk2(vig, vig);
+#pragma unroll
+    for(int k = 0; k < NP; k += 1) upk2(mul2(dst2[k], vig2), c[2 * k], c[2 * k + 1]);
+    if(NS & 1) c[NS - 1] = dst1 * vig;
 }
 
 /* film of one pixel held by a half warp: lane l16 owns wavelengths l16, l16+16, ...; when both halves work on the same
@@ -911,7 +948,7 @@ template <int NS> struct PixelFilm
     __device__ __forceinline__ void add(const float (&c)[NS])
     {
         cnt += 1.f; lit = true;
-        float inv = __frcp_rn(cnt);
+        float inv = r_rcp_fast(cnt);
         float delta[NS], rest[NS];
         v_add<NS>(sum, sum, c);
         v_sub<NS>(delta, c, mean);
@@ -924,7 +961,7 @@ template <int NS> struct PixelFilm
     {
         cnt += 1.f;
         if(!lit) return;
-        float inv = __frcp_rn(cnt);
+        float inv = r_rcp_fast(cnt);
 #pragma unroll
         for(int k = 0; k < NS; k += 1)
         {
@@ -993,7 +1030,10 @@ __device__ __noinline__ void film_store(FilmPtrs film, uint32_t gpix, uint32_t n
 
 /* ------------------------------------------------------------------ the kernel */
 
-template <typename R, int NS>
+/* ALLFAST: every surface material of the scene is a two-lobe plastic and there is exactly one light (decided by the
+ * host at scene upload: all shipped Cornell boxes except the gold/glass balls of cornell_plane_light).  The kernel then
+ * contains neither the general lobe evaluators nor the general shader. */
+template <typename R, int NS, bool ALLFAST>
 __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1005,6 +1045,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     off += (size_t)L.pool_words * 4;
     unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem_raw + off);
     off += 16 * 8;
+    off = (off + 15) & ~size_t(15);
     float *srec = reinterpret_cast<float *>(smem_raw + off);
 
     /* stage the scene once per (persistent) CTA */
@@ -1024,7 +1065,8 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lane16 = lane & (DRT_HALF - 1), half = lane >> 4;
-    float *rec = srec + (size_t)warp * L.path_words * DRT_WARP;
+    float *rec = srec + (size_t)warp * L.path_stride * DRT_WARP;   /* word w of slot s at rec[s * path_stride + w] */
+    const uint32_t stride = L.path_stride;
     const float *pool_lane = spool + lane16;
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
@@ -1034,10 +1076,6 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     /* one pixel per task (spp >= 32): both half warps shade samples of that pixel, two paths at a time.
      * several pixels per task (spp < 32): the lower half walks all slots and handles the pixel boundaries alone. */
     const bool paired = L.pixels_per_task == 1;
-
-    float e0[NS];   /* emission of light 0, kept in registers for the whole kernel */
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) e0[k] = (L.nlights > 0) ? pool_lane[ix.row[g.mat[g.light_surf[0]]][DRT_SPD_EMISSION] + k * DRT_HALF] : 0.f;
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
     uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
@@ -1067,7 +1105,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
             {
                 uint32_t lp = p_begin, s = q;
                 if(!paired) { lp += q / spp; s = q % spp; }
-                uint32_t r = trace_path<R>(g, ix, L, rec + lane, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
+                uint32_t r = trace_path<R, ALLFAST>(g, ix, L, rec + lane * stride, L.x0 + lp % rw, L.y0 + lp / rw, L.sample_begin + s, tally);
                 bin = r & 255u; general = r >> 8;
             }
             __syncwarp();
@@ -1079,7 +1117,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
             }
             /* ---- phase 2: half warp = path, lane16 = wavelength ---- */
             const uint32_t count = min((uint32_t)DRT_WARP, total - q0);
-            const uint32_t my_nb = __float_as_uint(rec[REC_NB * DRT_WARP + lane]);
+            const uint32_t my_nb = __float_as_uint(rec[lane * stride + REC_NB]);
             if(paired)
             {
                 /* K5, warp scope: order the batch so that the two halves of the warp get paths of like cost.  Key = inactive
@@ -1112,7 +1150,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                         {
                             if(L.record_dump)
                                 for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
-                                    L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
+                                    L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[slot * stride + wd];
                             if(L.path_dump)
                                 for(uint32_t wl = lane16; wl < n; wl += DRT_HALF) L.path_dump[((size_t)cur_lp * spp + q0 + slot) * n + wl] = 0.f;
                         }
@@ -1126,11 +1164,11 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                     if(pos < count)
                     {
                         float c[NS];
-                        replay_path<NS>(rec + slot, nb, g, ix, pool_lane, L, e0, c);
+                        replay_path<NS, ALLFAST>(rec + slot * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
                         film.add(c);
                         if(L.record_dump)
                             for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
-                                L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[wd * DRT_WARP + slot];
+                                L.record_dump[((size_t)cur_lp * spp + q0 + slot) * L.path_words + wd] = rec[slot * stride + wd];
                         if(L.path_dump)
                         {
 #pragma unroll
@@ -1169,12 +1207,12 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                     }
                     else
                     {
-                        replay_path<NS>(rec + i, nb, g, ix, pool_lane, L, e0, c);
+                        replay_path<NS, ALLFAST>(rec + i * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
                         film.add(c);
                     }
                     if(L.record_dump)
                         for(uint32_t wd = lane16; wd < L.path_words; wd += DRT_HALF)
-                            L.record_dump[((size_t)cur_lp * spp + cur_s) * L.path_words + wd] = rec[wd * DRT_WARP + i];
+                            L.record_dump[((size_t)cur_lp * spp + cur_s) * L.path_words + wd] = rec[i * stride + wd];
                     if(L.path_dump)
                     {
 #pragma unroll
@@ -1213,15 +1251,15 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
 
 /* ------------------------------------------------------------------ launch helper used by drt_capi.cu */
 
-template <typename R>
+template <typename R, bool ALLFAST>
 static cudaError_t launch_render_ns(const RenderLaunch &L, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
 #define DRT_LAUNCH(NS) do { \
-        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS, ALLFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if(e != cudaSuccess) return e; \
-        e = cudaFuncSetAttribute(drt::render_kernel<R, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        e = cudaFuncSetAttribute(drt::render_kernel<R, NS, ALLFAST>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         if(e != cudaSuccess) return e; \
-        drt::render_kernel<R, NS><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
+        drt::render_kernel<R, NS, ALLFAST><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
     switch(nslots)   /* wavelength slots per lane of a half warp: N <= 32, 48, 80, 128 */
     {
         case 2: DRT_LAUNCH(2); break;
@@ -1233,9 +1271,11 @@ static cudaError_t launch_render_ns(const RenderLaunch &L, int nslots, int grid,
     return cudaGetLastError();
 }
 
-cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
+/* f64 geometry is the branch-flip diagnostic: it always runs the general kernel */
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
-    return f64_geometry ? launch_render_ns<double>(L, nslots, grid, warps, smem, stream) : launch_render_ns<float>(L, nslots, grid, warps, smem, stream);
+    if(f64_geometry) return launch_render_ns<double, false>(L, nslots, grid, warps, smem, stream);
+    return all_fast ? launch_render_ns<float, true>(L, nslots, grid, warps, smem, stream) : launch_render_ns<float, false>(L, nslots, grid, warps, smem, stream);
 }
 
 size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps)
@@ -1245,6 +1285,7 @@ size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps
     off += (sizeof(SpdIndex) + 15) & ~size_t(15);
     off += (size_t)L.pool_words * 4;
     off += 16 * 8;
-    off += (size_t)warps * L.path_words * DRT_WARP * 4;
+    off = (off + 15) & ~size_t(15);
+    off += (size_t)warps * L.path_stride * DRT_WARP * 4;
     return off;
 }
