@@ -41,6 +41,8 @@ template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b)
     return mk<R>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
+/* MUFU.RCP alone (<= 1 ulp), for arguments known to be in range */
+__device__ __forceinline__ float r_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float  r_sqrt(float x)  { return sqrtf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float  r_abs(float x)   { return fabsf(x); }
@@ -185,48 +187,61 @@ __device__ __forceinline__ double hit_plane(V3<double> o, V3<double> d, R4<doubl
     bool inside = l >= 0.0 && 0.0 <= ju && ju <= u4.w && 0.0 <= jv && jv <= v4.w;
     return inside ? l : Num<double>::inf();
 }
-/* f32: same test; the in-plane offset is formed as d*l - (p - o), which reuses p - o (3 instructions fewer, same value up
- * to rounding) */
-__device__ __forceinline__ float hit_plane(V3<float> o, V3<float> d, R4<float> n4, R4<float> p4, R4<float> u4, R4<float> v4)
+/* f32: the same test fused with the nearest-so-far update.  The in-plane offset is formed as d*l - (p - o), which reuses p - o;
+ * l = ((p - o).n) / (d.n) uses MUFU.RCP without the range scaling of a full divide (|d.n| <= 1); the five inclusive bounds
+ * l >= 0, 0 <= j.u^ <= |u|, 0 <= j.v^ <= |v| (Q21) collapse into one minimum that must be >= 0 (FMNMX3).  A ray parallel to
+ * the plane (d.n == 0, geometry.c:160) gives l = +-inf or NaN: -inf fails the minimum, +inf and NaN fail l < best. */
+__device__ __forceinline__ bool hit_plane_nearer(V3<float> o, V3<float> d, R4<float> n4, R4<float> p4, R4<float> u4, R4<float> v4, float best, float &l)
 {
     V3<float> n = mk<float>(n4.x, n4.y, n4.z);
     float dn = dot(d, n);
     V3<float> po = mk<float>(p4.x - o.x, p4.y - o.y, p4.z - o.z);
-    float l = dot(po, n) / dn;
+    l = dot(po, n) * r_rcp_fast(dn);
     V3<float> j = mk<float>(fmaf(d.x, l, -po.x), fmaf(d.y, l, -po.y), fmaf(d.z, l, -po.z));
     float ju = dot(j, mk<float>(u4.x, u4.y, u4.z));
     float jv = dot(j, mk<float>(v4.x, v4.y, v4.z));
-    bool inside = dn != 0.f && l >= 0.f && 0.f <= ju && ju <= u4.w && 0.f <= jv && jv <= v4.w;
-    return inside ? l : Num<float>::inf();
+    float m = fminf(fminf(ju, u4.w - ju), fminf(fminf(jv, v4.w - jv), l));
+    return m >= 0.f && l < best;
+}
+__device__ __forceinline__ bool hit_plane_nearer(V3<double> o, V3<double> d, R4<double> n4, R4<double> p4, R4<double> u4, R4<double> v4, double best, double &l)
+{
+    l = hit_plane(o, d, n4, p4, u4, v4);
+    return l < best;
 }
 
-/* Nearest surface strictly closer than `limit` along the ray, or -1 (the loops of find_ray_intersection
- * daily_ray_trace.c:340-364 and points_mutually_visible :246-268; points are skipped, strict < keeps the lowest index
- * on ties).  One shared out-of-line body serves closest-hit (limit = inf) and shadow rays (limit = vis_dist). */
-template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, R *dist_out)
+/* Nearest surface strictly closer than `limit` along the ray: its SLOT in the regrouped arrays, or -1 (the loops of
+ * find_ray_intersection daily_ray_trace.c:340-364 and points_mutually_visible :246-268; points are skipped, strict < keeps
+ * the lowest scene index on ties).  One shared out-of-line body serves closest-hit (limit = inf) and shadow rays
+ * (limit = vis_dist).
+ * `skip` = slot of the PLANE the ray starts on, or -1.  The reference tests that plane too and always misses it: the origin
+ * is pushed 1e-4 along the ray first (Q2), so the plane lies at l = -1e-4 < 0 whatever the direction.  Its f64 rounding
+ * cannot change that sign; f32 rounding at grazing angles could, so not testing the plane is both cheaper and closer to the
+ * reference. */
+template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, int skip, R *dist_out)
 {
     R best = limit;
-    int found = 1 << 30;   /* scene index of the nearest surface so far */
-    /* planes, then spheres: no type switch inside the loops.  A candidate replaces the current one when it is strictly
-     * nearer, or equally near with a lower scene index -- the result of the reference's single in-order loop. */
+    int found = -1;
+    /* planes, then spheres: no type switch inside the loops.  Slots of one type are in scene order, so inside a loop a strict
+     * < reproduces the reference's single in-order loop; a sphere that ties with the current best replaces it only if its
+     * scene index is lower (a plane listed after that sphere). */
     const int np = g.nplanes, ns = g.nspheres;
 #pragma unroll 1
     for(int k = 0; k < np; k += 1)
     {
-        R dist = hit_plane(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k]);
-        int id = g.sid[k];
-        if(dist < best || (dist == best && dist < limit && id < found)) { best = dist; found = id; }
+        if(k == skip) continue;
+        R dist;
+        if(hit_plane_nearer(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k], best, dist)) { best = dist; found = k; }
     }
 #pragma unroll 1
     for(int k = np; k < np + ns; k += 1)
     {
         R4<R> p4 = g.P4[k];
         R dist = hit_sphere(o, d, mk<R>(p4.x, p4.y, p4.z), p4.w);
-        int id = g.sid[k];
-        if(dist < best || (dist == best && dist < limit && id < found)) { best = dist; found = id; }
+        bool tie = dist == best && dist < limit && found >= 0 && g.sid[k] < g.sid[found];
+        if(dist < best || tie) { best = dist; found = k; }
     }
     *dist_out = best;
-    return (found == (1 << 30)) ? -1 : found;
+    return found;
 }
 
 template <typename R> struct Hit
@@ -234,15 +249,18 @@ template <typename R> struct Hit
     V3<R> pos, nrm, out;
     R on_dot;
     int surf_mat, inc_mat, trans_mat;
+    int plane_slot;   /* slot of the plane that was hit (nearest_surface's `skip` for the rays leaving this point), -1 for a sphere */
 };
 
 /* find_ray_intersection, daily_ray_trace.c:334-403.  Returns false on a miss (escape material). */
-template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R> &g, V3<R> o, V3<R> d, Hit<R> &h)
+template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R> &g, V3<R> o, V3<R> d, int skip, Hit<R> &h)
 {
     o = o + d * Num<R>::fudge();   /* Q2 */
     R best;
-    int found = nearest_surface<R>(g, o, d, Num<R>::inf(), &best);
-    if(found < 0) return false;
+    int slot = nearest_surface<R>(g, o, d, Num<R>::inf(), skip, &best);
+    if(slot < 0) return false;
+    const int found = g.sid[slot];
+    h.plane_slot = (slot < g.nplanes) ? slot : -1;
     h.pos = o + d * best;
     V3<R> n = mk<R>(g.nx[found], g.ny[found], g.nz[found]);
     bool is_plane = g.type[found] == DRT_GEO_PLANE;
@@ -262,14 +280,14 @@ template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R>
 }
 
 /* points_mutually_visible, daily_ray_trace.c:238-270 */
-template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g, V3<R> p0, V3<R> p1)
+template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g, V3<R> p0, V3<R> p1, int skip)
 {
     V3<R> dir = normalise(p1 - p0);
     V3<R> o = p0 + dir * Num<R>::fudge();
     V3<R> po = p1 - o;
     R vis_dist = r_sqrt(dot(po, po)) - Num<R>::fudge();
     R t;
-    return nearest_surface<R>(g, o, dir, vis_dist, &t) < 0;
+    return nearest_surface<R>(g, o, dir, vis_dist, skip, &t) < 0;
 }
 
 /* ------------------------------------------------------------------ BSDF evaluation reduced to basis weights
@@ -607,12 +625,13 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     rec[REC_VIG] = (float)dot(d, fwd);   /* Q20 */
 
     uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth, general = 0;
+    int skip = -1;
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
     for(uint32_t depth = 0; depth < L.max_depth; depth += 1)
     {
         Hit<R> h;
         closest += 1;
-        bool found = closest_hit<R>(g, o, d, h);
+        bool found = closest_hit<R>(g, o, d, skip, h);
         int m = found ? h.surf_mat : g.escape_mat;
         int flags = g.mflags[m];
         uint32_t base = REC_HEAD + nb * bw;
@@ -667,7 +686,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                 k = g.light_pdf[ls];
             }
             shadow += 1;
-            if(visible<R>(g, h.pos, lp))
+            if(visible<R>(g, h.pos, lp, h.plane_slot))
             {
                 const uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
                 const V3<R> ldir = normalise(lp - h.pos);
@@ -705,6 +724,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         nb += 1;
         d = in;
         o = h.pos;
+        skip = h.plane_slot;
     }
     rec[REC_NB] = __uint_as_float(nb);
     tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
@@ -723,9 +743,6 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
 { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
 { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
-/* MUFU.RCP alone (<= 1 ulp): the sample count of the Welford update is a small positive integer */
-__device__ __forceinline__ float r_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 /* o = a*b + c,  o = s*b + c,  o = a*b,  o = s*b  over NS wavelength slots */
 template <int NS> __device__ __forceinline__ void v_fma(float (&o)[NS], const float (&a)[NS], const float (&b)[NS], const float (&c)[NS])
@@ -1078,7 +1095,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     const bool paired = L.pixels_per_task == 1;
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
-    uint32_t hist = 0, traced = 0;            /* lane d < 9 counts paths that ended in histogram bin d */
+    uint32_t traced = 0;
     for(;;)
     {
         uint32_t task = 0;
@@ -1109,15 +1126,25 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                 bin = r & 255u; general = r >> 8;
             }
             __syncwarp();
-#pragma unroll
-            for(uint32_t d = 0; d < 9; d += 1)
             {
-                uint32_t votes = __popc(__ballot_sync(0xffffffffu, bin == d));
-                if(lane == d) hist += votes;
+                /* termination histogram: one shared-memory atomic per distinct bin of the batch (bin 9 = idle lane) */
+                const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                if(bin < 9u && lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(&s_stats[5 + bin], (unsigned long long)__popc(peers));
             }
             /* ---- phase 2: half warp = path, lane16 = wavelength ---- */
             const uint32_t count = min((uint32_t)DRT_WARP, total - q0);
             const uint32_t my_nb = __float_as_uint(rec[lane * stride + REC_NB]);
+            if(paired && !(L.path_dump || L.record_dump) && !__any_sync(0xffffffffu, lane < count && my_nb != 0u))
+            {
+                /* no path of the batch has a bounce record (every sample left the scene): nothing to replay */
+                if(half == 0)
+                {
+                    if(!film.lit) film.cnt += (float)count;
+                    else for(uint32_t i = 0; i < count; i += 1) film.add_zero();
+                }
+                __syncwarp();
+                continue;
+            }
             if(paired)
             {
                 /* K5, warp scope: order the batch so that the two halves of the warp get paths of like cost.  Key = inactive
@@ -1241,7 +1268,6 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
         if(lane == 0) atomicAdd(&s_stats[1 + k], v);
     }
     if(lane == 0) atomicAdd(&s_stats[0], (unsigned long long)traced);
-    if(lane < 9) atomicAdd(&s_stats[5 + lane], (unsigned long long)hist);
     __syncthreads();
     if(threadIdx.x < 14 && s_stats[threadIdx.x])
         atomicAdd(reinterpret_cast<unsigned long long *>(L.stats) + threadIdx.x, s_stats[threadIdx.x]);
