@@ -16,7 +16,8 @@
 #include "drt_device.cuh"
 
 cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps);
+int         drt_render_cta_warps(bool f64_geometry, bool all_fast);
+size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots);
 void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
 void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
@@ -355,15 +356,19 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     uint32_t spp = p->sample_end - p->sample_begin;
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
     L.eval_words = (uint32_t)ctx->eval_words;
+    const bool compact = ctx->all_fast && !ctx->f64_geometry;   /* the ALLFAST kernel and its compact records */
     L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
     if(L.bounce_words < 8) L.bounce_words = 8;
-    L.path_words = 4 + p->max_depth * L.bounce_words;
+    L.head_words = 4;
+    if(compact) { L.bounce_words = 4; L.head_words = (2 + (p->max_depth + 1) / 2 + 3u) & ~3u; }
+    L.path_words = L.head_words + p->max_depth * L.bounce_words;
     L.path_stride = ((L.path_words / 4) & 1u) ? L.path_words : L.path_words + 4;
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
-    int warps = DRT_CTA_WARPS;
-    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps);
-    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps); }
+    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, ctx->all_fast);
+    int warps = full_warps;
+    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots);
+    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); }
     if(smem > ctx->smem_optin)
         return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
                     p->max_depth, ctx->nlights, smem, ctx->smem_optin);
@@ -371,7 +376,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
 #ifndef DRT_MIN_CTAS
 #define DRT_MIN_CTAS 2
 #endif
-    int by_threads = (DRT_MIN_CTAS * DRT_CTA_WARPS) / warps;    /* register budget of __launch_bounds__(256, DRT_MIN_CTAS) */
+    int by_threads = (DRT_MIN_CTAS * full_warps) / warps;    /* register budget of the kernel's __launch_bounds__ */
     if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if(ctas_per_sm < 1) ctas_per_sm = 1;
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);

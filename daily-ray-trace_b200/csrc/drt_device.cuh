@@ -16,7 +16,9 @@
 #define DRT_MAX_SLOTS 4            /* ceil(DRT_MAX_WAVELENGTHS / 32): full-warp wavelength layout of the film epilogue kernels */
 #define DRT_HALF 16                /* phase 2 of the render kernel: a path is shaded by a HALF warp, lane l16 holds wavelengths l16 + 16k */
 #define DRT_MAX_HALF_SLOTS 8       /* ceil(DRT_MAX_WAVELENGTHS / 16) */
-#define DRT_CTA_WARPS 8
+#ifndef DRT_CTA_WARPS
+#define DRT_CTA_WARPS 8      /* warps per CTA of the general kernel */
+#endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 
 /* Spectral basis a BSDF evaluation is expressed in (eval_weights in drt_kernels.cu).  A material's lobe list fixes
@@ -97,7 +99,12 @@ struct DeviceStats
  *                         [0] header: kind(2) | 1<<2 | plastic block float4 index<<4
  *                         [1] w_diffuse * k  [2] w_glossy * k   (next-event estimation, 0 when the light is hidden)
  *                         [4] w_diffuse / pdf [5] w_glossy / pdf (sampled direction)
- *   bounce_words is a multiple of 4 and at least 8. */
+ *   bounce_words is a multiple of 4 and at least 8.
+ * Compact records of the ALLFAST kernel (every surface material a two-lobe plastic, one light):
+ *   word 0, 1         number of bounce records, vignette factor
+ *   from word 2       one 16-bit header per bounce: kind(2) | plastic block word offset (a multiple of 4), or kind | material<<2
+ *                     for a path that ran into an emitter
+ *   from head_words   per bounce { w_diffuse k, w_glossy k (next-event estimation), w_diffuse / pdf, w_glossy / pdf (sampled direction) } */
 struct RenderLaunch
 {
     const void     *geom;          /* GeomT<float> or GeomT<double> in global memory */
@@ -119,7 +126,8 @@ struct RenderLaunch
     uint32_t pixels_per_task;      /* contiguous rectangle pixels claimed per warp task */
     uint32_t eval_words;           /* stored weights per BSDF evaluation (scene-wide maximum) */
     uint32_t bounce_words;         /* 2 + nlights*(eval_words+1) + eval_words */
-    uint32_t path_words;           /* 4 + max_depth*bounce_words */
+    uint32_t head_words;           /* words before the first bounce: 4, or roundup4(2 + ceil(max_depth / 2)) for compact records */
+    uint32_t path_words;           /* head_words + max_depth*bounce_words */
     uint32_t path_stride;          /* words between the records of consecutive slots: >= path_words, 4 * odd */
     uint32_t geom_bytes, pool_words;
 };

@@ -575,7 +575,8 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 #endif
 #define REC_NB   0
 #define REC_VIG  1
-#define REC_HEAD 4
+#define REC_HDR16 2   /* ALLFAST records: 16-bit bounce headers from word 2 */
+#define REC_HEAD 4    /* general records: first bounce */
 #define KIND_SHADE 1u
 #define KIND_EMIT  2u
 /* bounce header word (record layout: RenderLaunch in drt_device.cuh):
@@ -639,7 +640,8 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         {
             if(flags & 2)
             {
-                rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
+                if(ALLFAST) reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)(KIND_EMIT | ((uint32_t)m << 2));
+                else rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
                 nb += 1;
             }
             end_depth = depth;
@@ -707,7 +709,13 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         float wd_s = 0.f, wg_s = 0.f;
         if(plastic) plastic_weights<R>(g, sm, h.nrm, h.out, in, (float)inv_pdf, wd_s, wg_s);
         else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, es);
-        if(fast)
+        if(ALLFAST)
+        {
+            /* compact record: four weights per bounce, the 16-bit header (kind | plastic block word offset, a multiple of 4) apart */
+            *reinterpret_cast<float4 *>(rec + L.head_words + 4u * nb) = make_float4(wd_n, wg_n, wd_s, wg_s);
+            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)(KIND_SHADE | (uint32_t)ix.plastic[sm]);
+        }
+        else if(fast)
         {
             float4 *r4 = reinterpret_cast<float4 *>(rec + base);
             r4[0] = make_float4(__uint_as_float(KIND_SHADE | HDR_FAST | ((uint32_t)ix.plastic[sm] << 2)), wd_n, wg_n, 0.f);
@@ -891,6 +899,44 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
     float thr1 = 1.f, dst1 = 0.f;
 #pragma unroll
     for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(1.f, 1.f); dst2[k] = pk2(0.f, 0.f); }
+    if constexpr(ALLFAST)
+    {
+        /* compact records (RenderLaunch in drt_device.cuh): header halves from word 2, four weights per bounce */
+        const uint16_t *hp = reinterpret_cast<const uint16_t *>(col + REC_HDR16);
+        const float4 *wp = reinterpret_cast<const float4 *>(col + L.head_words);
+        for(uint32_t b = 0; b < nb; b += 1)
+        {
+            const uint32_t hdr = hp[b];
+            if((hdr & 3u) != KIND_SHADE)   /* the path ran into an emitter, cast_ray :453-457 */
+            {
+                const float *row = pool_lane + ix.row[hdr >> 2][DRT_SPD_EMISSION];
+#pragma unroll
+                for(int k = 0; k < NP; k += 1) dst2[k] = fma2(thr2[k], pk2(row[(2 * k) * DRT_HALF], row[(2 * k + 1) * DRT_HALF]), dst2[k]);
+                if(NS & 1) dst1 = fmaf(thr1, row[(NS - 1) * DRT_HALF], dst1);
+                break;
+            }
+            const float4 w = wp[b];   /* wd_n k, wg_n k, wd_s / pdf, wg_s / pdf */
+            const float4 *blk = reinterpret_cast<const float4 *>(pool + (hdr & 0xfffcu)) + lane16;
+            const unsigned long long wdn = pk2(w.x, w.x), wgn = pk2(w.y, w.y), wds = pk2(w.z, w.z), wgs = pk2(w.w, w.w);
+#pragma unroll
+            for(int k = 0; k < NP; k += 1)
+            {
+                const float4 dg = blk[(2 * k) * DRT_HALF], ee = blk[(2 * k + 1) * DRT_HALF];
+                unsigned long long f = fma2(wgn, pk2(ee.z, ee.w), mul2(wdn, pk2(ee.x, ee.y)));
+                dst2[k] = fma2(thr2[k], f, dst2[k]);
+                unsigned long long t = fma2(wgs, pk2(dg.z, dg.w), mul2(wds, pk2(dg.x, dg.y)));
+                thr2[k] = mul2(thr2[k], t);
+            }
+            if(NS & 1)
+            {
+                const float4 q = blk[(NS - 1) * DRT_HALF];   /* D, G, DE, GE of the last slot */
+                dst1 = fmaf(thr1, fmaf(w.y, q.w, w.x * q.z), dst1);
+                thr1 *= fmaf(w.w, q.y, w.z * q.x);
+            }
+        }
+    }
+    else
+    {
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
     const float *p = col + REC_HEAD;
     uint32_t base = REC_HEAD;
@@ -900,7 +946,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
         const float4 a = a_next;
         if(b + 1 < nb) a_next = *reinterpret_cast<const float4 *>(p + bw);   /* next header in flight while this bounce is shaded */
         const uint32_t hdr = __float_as_uint(a.x);
-        if(ALLFAST ? ((hdr & 3u) == KIND_SHADE) : ((hdr & HDR_FAST) != 0u))
+        if((hdr & HDR_FAST) != 0u)
         {
             const float4 s4 = *reinterpret_cast<const float4 *>(p + 4);
             const float4 *blk = reinterpret_cast<const float4 *>(pool) + (hdr >> 4) + lane16;
@@ -922,7 +968,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
             }
             continue;
         }
-        if(ALLFAST || (hdr & 3u) == KIND_EMIT)   /* the path ran into an emitter, cast_ray :453-457 */
+        if((hdr & 3u) == KIND_EMIT)   /* the path ran into an emitter, cast_ray :453-457 */
         {
             const float *row = pool_lane + ix.row[(hdr >> 3) & 31][DRT_SPD_EMISSION];
 #pragma unroll
@@ -942,6 +988,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
             if(NS & 1) { thr1 = st.thr.v[NS - 1]; dst1 = st.dst.v[NS - 1]; }
         }
     }
+    }
     const float vig = col[REC_VIG];
     const unsigned long long vig2 = pk2(vig, vig);
 #pragma unroll
@@ -960,6 +1007,21 @@ template <int NS> struct PixelFilm
         cnt = 0.f; lit = false;
 #pragma unroll
         for(int k = 0; k < NS; k += 1) { sum[k] = 0.f; mean[k] = 0.f; m2[k] = 0.f; }
+    }
+    /* The film is live for all samples of the pixel but idle while the warp traces (phase 1, the register-hungry phase): it is
+     * parked in shared memory for the duration, word w of lane l at s[w*32 + l], which lowers the kernel's register need
+     * and so raises the number of resident warps. */
+    __device__ __forceinline__ void park(float *s) const
+    {
+        s[0] = cnt; s[DRT_WARP] = lit ? 1.f : 0.f;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) { s[(2 + k) * DRT_WARP] = sum[k]; s[(2 + NS + k) * DRT_WARP] = mean[k]; s[(2 + 2 * NS + k) * DRT_WARP] = m2[k]; }
+    }
+    __device__ __forceinline__ void unpark(const float *s)
+    {
+        cnt = s[0]; lit = s[DRT_WARP] != 0.f;
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) { sum[k] = s[(2 + k) * DRT_WARP]; mean[k] = s[(2 + NS + k) * DRT_WARP]; m2[k] = s[(2 + 2 * NS + k) * DRT_WARP]; }
     }
     /* K6: film accumulation + Welford, daily_ray_trace.c:732-743 (filter weight is the constant 1, Q20) */
     __device__ __forceinline__ void add(const float (&c)[NS])
@@ -1050,8 +1112,11 @@ __device__ __noinline__ void film_store(FilmPtrs film, uint32_t gpix, uint32_t n
 /* ALLFAST: every surface material of the scene is a two-lobe plastic and there is exactly one light (decided by the
  * host at scene upload: all shipped Cornell boxes except the gold/glass balls of cornell_plane_light).  The kernel then
  * contains neither the general lobe evaluators nor the general shader. */
+#ifndef DRT_FAST_WARPS
+#define DRT_FAST_WARPS 16   /* warps per CTA of the ALLFAST kernel: 2 CTAs x 16 warps x 64 registers fill an SM (measured: 8 -> 16 warps = +21 % paths/s) */
+#endif
 template <typename R, int NS, bool ALLFAST>
-__global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
@@ -1064,6 +1129,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     off += 16 * 8;
     off = (off + 15) & ~size_t(15);
     float *srec = reinterpret_cast<float *>(smem_raw + off);
+    float *spark = srec + (size_t)(blockDim.x >> 5) * L.path_stride * DRT_WARP;   /* film parking, (3 NS + 2) * 32 words per warp */
 
     /* stage the scene once per (persistent) CTA */
     {
@@ -1084,6 +1150,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
     const uint32_t lane16 = lane & (DRT_HALF - 1), half = lane >> 4;
     float *rec = srec + (size_t)warp * L.path_stride * DRT_WARP;   /* word w of slot s at rec[s * path_stride + w] */
     const uint32_t stride = L.path_stride;
+    float *park = spark + (size_t)warp * (3 * NS + 2) * DRT_WARP + lane;
     const float *pool_lane = spool + lane16;
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
@@ -1116,6 +1183,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
             /* ---- phase 1: lane = path ---- */
+            if(ALLFAST) film.park(park);   /* the general kernel is bound by its 128-register code either way */
             uint32_t q = q0 + lane;
             uint32_t bin = 9, general = 0;
             if(q < total)
@@ -1126,6 +1194,7 @@ __global__ void __launch_bounds__(DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(c
                 bin = r & 255u; general = r >> 8;
             }
             __syncwarp();
+            if(ALLFAST) film.unpark(park);
             {
                 /* termination histogram: one shared-memory atomic per distinct bin of the batch (bin 9 = idle lane) */
                 const uint32_t peers = __match_any_sync(0xffffffffu, bin);
@@ -1304,7 +1373,9 @@ cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all
     return all_fast ? launch_render_ns<float, true>(L, nslots, grid, warps, smem, stream) : launch_render_ns<float, false>(L, nslots, grid, warps, smem, stream);
 }
 
-size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps)
+int drt_render_cta_warps(bool f64_geometry, bool all_fast) { return (!f64_geometry && all_fast) ? DRT_FAST_WARPS : DRT_CTA_WARPS; }
+
+size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots)
 {
     size_t geom = f64_geometry ? sizeof(GeomT<double>) : sizeof(GeomT<float>);
     size_t off = (geom + 15) & ~size_t(15);
@@ -1313,5 +1384,6 @@ size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps
     off += 16 * 8;
     off = (off + 15) & ~size_t(15);
     off += (size_t)warps * L.path_stride * DRT_WARP * 4;
+    off += (size_t)warps * (3 * (size_t)nslots + 2) * DRT_WARP * 4;   /* film parking */
     return off;
 }

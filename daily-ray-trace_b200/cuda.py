@@ -40,7 +40,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(PACKAGE_DIR, "libdrt_cuda.so")
+    """libdrt_cuda.so next to this file; DRT_CUDA_LIB names another build of the same library (A/B measurements)."""
+    return os.environ.get("DRT_CUDA_LIB") or os.path.join(PACKAGE_DIR, "libdrt_cuda.so")
 
 
 def lib():
