@@ -145,20 +145,46 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         if(s->materials[f->material].is_emissive) g->light_surf[nl++] = i;
     }
     g->nlights = nl;
-    /* packed copies regrouped by type for the intersection loops */
+    /* packed copies regrouped by type for the intersection loops: x-, y-, z-aligned rectangles, other planes, spheres */
+    auto plane_axis = [&](const drt_surface *f) -> int {
+        auto single = [](const double *v) -> int {
+            int axis = -1;
+            for(int k = 0; k < 3; k += 1) if(v[k] != 0.0) { if(axis >= 0) return -1; axis = k; }
+            return axis;
+        };
+        int a = single(f->normal), b = single(f->u), c = single(f->v);
+        if(a < 0 || b < 0 || c < 0 || a == b || a == c || b == c) return -1;
+        if(f->normal[a] != 1.0 && f->normal[a] != -1.0) return -1;
+        return a;
+    };
     int slot = 0;
-    for(int pass = 0; pass < 2; pass += 1)
+    for(int pass = 0; pass < 5; pass += 1)
         for(int i = 0; i < s->num_surfaces; i += 1)
         {
-            int want = pass == 0 ? DRT_GEO_PLANE : DRT_GEO_SPHERE;
-            if(s->surfaces[i].type != want) continue;
+            const drt_surface *f = &s->surfaces[i];
+            if(pass < 4) { if(f->type != DRT_GEO_PLANE || plane_axis(f) != (pass < 3 ? pass : -1)) continue; }
+            else if(f->type != DRT_GEO_SPHERE) continue;
             g->sid[slot] = i;
             g->N4[slot] = R4<R>{ g->nx[i], g->ny[i], g->nz[i], (R)0 };
             g->P4[slot] = R4<R>{ g->px[i], g->py[i], g->pz[i], g->rad[i] };
             g->U4[slot] = R4<R>{ g->unx[i], g->uny[i], g->unz[i], g->ulen[i] };
             g->V4[slot] = R4<R>{ g->vnx[i], g->vny[i], g->vnz[i], g->vlen[i] };
+            if(pass < 3)
+            {
+                const int a = pass, b = (a == 0) ? 1 : 0, c = (a == 2) ? 1 : 2;   /* in-plane axes b < c */
+                double lo[2], hi[2];
+                const int bc[2] = { b, c };
+                for(int k = 0; k < 2; k += 1)
+                {
+                    double p0 = f->position[bc[k]], p1 = p0 + f->u[bc[k]] + f->v[bc[k]];   /* one of u, v lies along this axis */
+                    lo[k] = p0 < p1 ? p0 : p1; hi[k] = p0 < p1 ? p1 : p0;
+                }
+                g->AX4[slot] = R4<R>{ (R)f->position[a], (R)(0.5 * (lo[0] + hi[0])), (R)(0.5 * (hi[0] - lo[0])), (R)(0.5 * (lo[1] + hi[1])) };
+                g->AXH[slot] = R2<R>{ (R)(0.5 * (hi[1] - lo[1])), (R)i };
+                g->nax[a] += 1;
+            }
             slot += 1;
-            if(pass == 0) g->nplanes += 1; else g->nspheres += 1;
+            if(pass < 4) g->nplanes += 1; else g->nspheres += 1;
         }
     for(int m = 0; m < s->num_materials; m += 1)
     {

@@ -28,13 +28,20 @@ enum { BK_CONST = 0, BK_DIFFUSE, BK_GLOSSY, BK_MIRROR, BK_DIEL_R, BK_COND_ON, BK
 
 /* one surface as four 16-byte (f32) / 32-byte (f64) vectors, so that the intersection loop issues vector shared-memory loads */
 template <typename R> struct alignas(16) R4 { R x, y, z, w; };
+template <typename R> struct alignas(8) R2 { R x, y; };
 
 template <typename R>
 struct GeomT
 {
     /* intersectable surfaces regrouped by type: slots [0, nplanes) are planes, [nplanes, nplanes + nspheres) spheres;
-     * sid[slot] is the surface's index in the scene (ties in distance go to the lower scene index, Q21) */
+     * sid[slot] is the surface's index in the scene (ties in distance go to the lower scene index, Q21).
+     * The planes come in four groups: axis-aligned rectangles with normal +-x, +-y, +-z (nax[0..2] of them, every Cornell
+     * wall), then planes in general position.  An axis-aligned rectangle with normal axis a and in-plane axes b < c is
+     * AX4[slot] = { p_a, centre_b, half extent_b, centre_c }, AXH[slot] = { half extent_c, scene index as a number }. */
     int   nplanes, nspheres, pad2, pad3;
+    int   nax[4];                  /* [3] unused */
+    R4<R> AX4[DRT_MAX_SURFACES];
+    R2<R> AXH[DRT_MAX_SURFACES];
     int   sid[DRT_MAX_SURFACES];
     R4<R> N4[DRT_MAX_SURFACES];    /* plane normal | w unused */
     R4<R> P4[DRT_MAX_SURFACES];    /* position | w = sphere radius */

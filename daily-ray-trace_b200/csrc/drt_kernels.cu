@@ -217,28 +217,63 @@ __device__ __forceinline__ bool hit_plane_nearer(V3<double> o, V3<double> d, R4<
  * is pushed 1e-4 along the ray first (Q2), so the plane lies at l = -1e-4 < 0 whatever the direction.  Its f64 rounding
  * cannot change that sign; f32 rounding at grazing angles could, so not testing the plane is both cheaper and closer to the
  * reference. */
+__device__ __forceinline__ float  r_rcp(float x)  { return r_rcp_fast(x); }
+__device__ __forceinline__ double r_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float  r_min3(float a, float b, float c)    { return fminf(fminf(a, b), c); }   /* FMNMX3 */
+__device__ __forceinline__ double r_min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
+
+/* One group of axis-aligned rectangles (normal along axis a; in-plane axes b < c): l = (p_a - o_a) / d_a and the hit point's
+ * two in-plane coordinates against the rectangle's centre and half extents -- line_plane_intersection (geometry.c:157-182)
+ * with the zero terms of its dot products dropped.  o?, d? are the ray's components along a, b, c; inv_da = 1 / d_a.
+ * A ray parallel to the plane gives l = +-inf or NaN, which fail l >= 0 or l < best as in hit_plane_nearer. */
+template <typename R>
+__device__ __forceinline__ void nearest_axis_group(const GeomT<R> &g, int k0, int k1, R oa, R ob, R oc, R inv_da, R db, R dc, int skip,
+                                                   R &best, R &best_sid, int &found)
+{
+#pragma unroll 1
+    for(int k = k0; k < k1; k += 1)
+    {
+        const R4<R> q = g.AX4[k];
+        const R2<R> h = g.AXH[k];
+        const R l = (q.x - oa) * inv_da;
+        const R eb = q.z - r_abs((ob + db * l) - q.y);
+        const R ec = h.x - r_abs((oc + dc * l) - q.w);
+        const R m = r_min3(eb, ec, l);
+        /* nearer, or as near as the best so far but earlier in the scene (best_sid is -1 until something is found) */
+        const bool take = (m >= R(0)) & ((l < best) | ((l == best) & (h.y < best_sid))) & (k != skip);   /* & and |: no branches */
+        best = take ? l : best; best_sid = take ? h.y : best_sid; found = take ? k : found;
+    }
+}
+
 template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, int skip, R *dist_out)
 {
-    R best = limit;
+    R best = limit, best_sid = R(-1);
     int found = -1;
-    /* planes, then spheres: no type switch inside the loops.  Slots of one type are in scene order, so inside a loop a strict
-     * < reproduces the reference's single in-order loop; a sphere that ties with the current best replaces it only if its
-     * scene index is lower (a plane listed after that sphere). */
+    /* rectangles by axis, planes in general position, spheres: no type switch inside the loops.  Slots of one group are in
+     * scene order, so inside a group a strict < reproduces the reference's single in-order loop; a candidate that ties with
+     * the current best (coplanar surfaces, a ray through a shared edge) replaces it only if its scene index is lower. */
+    const int nx = g.nax[0], ny = nx + g.nax[1], nz = ny + g.nax[2];
     const int np = g.nplanes, ns = g.nspheres;
+    nearest_axis_group<R>(g, 0, nx, o.x, o.y, o.z, r_rcp(d.x), d.y, d.z, skip, best, best_sid, found);
+    nearest_axis_group<R>(g, nx, ny, o.y, o.x, o.z, r_rcp(d.y), d.x, d.z, skip, best, best_sid, found);
+    nearest_axis_group<R>(g, ny, nz, o.z, o.x, o.y, r_rcp(d.z), d.x, d.y, skip, best, best_sid, found);
 #pragma unroll 1
-    for(int k = 0; k < np; k += 1)
+    for(int k = nz; k < np; k += 1)
     {
         if(k == skip) continue;
         R dist;
-        if(hit_plane_nearer(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k], best, dist)) { best = dist; found = k; }
+        const R sid = R(g.sid[k]);
+        bool nearer = hit_plane_nearer(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k], best, dist);
+        if(!nearer && dist == best && sid < best_sid) nearer = hit_plane_nearer(o, d, g.N4[k], g.P4[k], g.U4[k], g.V4[k], limit, dist);
+        if(nearer) { best = dist; best_sid = sid; found = k; }
     }
 #pragma unroll 1
     for(int k = np; k < np + ns; k += 1)
     {
         R4<R> p4 = g.P4[k];
         R dist = hit_sphere(o, d, mk<R>(p4.x, p4.y, p4.z), p4.w);
-        bool tie = dist == best && dist < limit && found >= 0 && g.sid[k] < g.sid[found];
-        if(dist < best || tie) { best = dist; found = k; }
+        const R sid = R(g.sid[k]);
+        if(dist < best || (dist == best && sid < best_sid)) { best = dist; best_sid = sid; found = k; }
     }
     *dist_out = best;
     return found;

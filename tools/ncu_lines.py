@@ -56,9 +56,19 @@ print(f"total {tot / paths:.1f} warp-instr/path, {len(data)} SASS instructions")
 for (f, ln), (ex, sm, thr, cnt) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
     text = text_of(f, ln)
     print(f"{f[:14]:14s}{ln:5d} {ex / paths:6.2f}/path {100 * ex / tot:5.1f}% smp {100 * sm / totS:5.1f}% thr {thr / max(ex, 1):4.1f} sass {cnt:4d} | {text}")
-RANGES = [(31, 107, "vector algebra (inlined)"), (108, 136, "rng"), (137, 231, "nearest_surface / hit_*"), (232, 274, "closest_hit / visible"),
-          (275, 384, "eval_weights"), (385, 418, "fresnel"), (419, 559, "samplers"), (560, 698, "trace_path"), (699, 749, "packed ops"),
-          (750, 897, "replay"), (898, 993, "film"), (994, 1300, "kernel body")]
+# regions of drt_kernels.cu, found by their section markers so that the table follows the source
+MARKS = [("small vector algebra", "vector algebra (inlined)"), ("per-path random stream", "rng"), ("K2: closest hit", "nearest_surface / hit_*"),
+         ("template <typename R> struct Hit", "closest_hit / visible"), ("BSDF evaluation reduced to basis weights", "eval weights"),
+         ("dielectric Fresnel at one wavelength", "fresnel"), ("K4: the six direction samplers", "samplers"),
+         ("path records in shared memory", "trace_path"), ("packed f32x2 arithmetic", "packed ops"),
+         ("phase 2: spectral replay", "replay"), ("film of one pixel held by a half warp", "film"), ("the kernel */", "kernel body")]
+text_of("drt_kernels.cu", 1)
+RANGES = []
+for key, name in MARKS:
+    at = next((i + 1 for i, l in enumerate(srcs["drt_kernels.cu"]) if key in l), None)
+    if at: RANGES.append([at, 10**9, name])
+RANGES.sort()
+for i in range(len(RANGES) - 1): RANGES[i][1] = RANGES[i + 1][0] - 1
 for (f, ln), (ex, sm, thr, cnt) in per_line.items():
     name = f
     if f == "drt_kernels.cu":
