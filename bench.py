@@ -110,6 +110,17 @@ def _cpu_worker_render(job):
     return (y1 - y0) * w
 
 
+def _cpu_worker_tile(job):
+    """Per-path spectra [(pixels), samples, N] of a pixel rectangle through the reference's sample_scene (same per-path streams)."""
+    x0, y0, x1, y1, s0, s1 = job
+    w, h = _W["dims"]
+    if _W["kind"] == "reference":
+        return _W["ref"].render_tile(x0, y0, x1, y1, s0, s1, want_paths=True)[3]
+    od, sc, cam, cfg = _W["oracle"]
+    prm = od.params(w, h, s0, s1, _W["depth"], cfg.pixel_scheme, _W["seed"])
+    return od.render_tile(sc, cam, prm, x0, y0, x1, y1, want_paths=True)[3]
+
+
 class CpuArm:
     """The reference's CPU implementation of the path on all host cores: one single-threaded process per core (the
     reference has global RNG/scratch state), rows of the image split between them."""
@@ -132,6 +143,11 @@ class CpuArm:
         t0 = time.perf_counter()
         paths = sum(self.pool.map(_cpu_worker_render, jobs, chunksize=1))
         return paths, time.perf_counter() - t0
+
+    def tile_paths(self, x0, y0, x1, y1, s0, s1):
+        import numpy as np
+        rows = self.pool.map(_cpu_worker_tile, [(x0, y, x1, y + 1, s0, s1) for y in range(y0, y1)], chunksize=1)
+        return np.concatenate(rows, axis=0)
 
     def close(self):
         self.pool.close()
@@ -357,6 +373,7 @@ def run_b200_arm(a):
     d2h_bytes = (3 * npix * n + npix) * 4
 
     if rank == 0:
+        kinfo = ctx.render_kernel_info(a.depth)
         flops_path, rc, rs, b = algorithmic_flops_per_path(scene, st, n)
         paths_launch = a.width * a.height * a.spp
         achieved_tf = flops_path * paths_launch / (kernel_ms * 1e-3) / 1e12
@@ -392,7 +409,7 @@ def run_b200_arm(a):
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (profiles/ncu_traffic.json); null for other image sizes",
-                         "kernel": "drt::render_kernel<float,5>" if a.geometry == "f32" else "drt::render_kernel<double,5>", "kernel_ms": kernel_ms,
+                         "kernel": kinfo[0], "warps_per_cta": kinfo[1], "ctas_per_sm": kinfo[2], "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_path": flops_path,
                          "peak_source": "measured in this run by drt_cuda_measure_fp32_peak (FFMA, 2 flops); MEASURED_PEAKS.json has no FP32 entry",
                          "hbm": {"achieved": film_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -405,11 +422,29 @@ def run_b200_arm(a):
                 arm.step(0, rows=max(64, a.height // 8))
                 paths, secs = 0, 0.0
                 passes = 0
-                while secs < 8.0 and passes < 8:
+                while secs < 10.0 and passes < 256:   # a bounded sample: about 10 s of work on all host cores
                     p, t = arm.step(1 + passes)
                     paths += p
                     secs += t
                     passes += 1
+                # image RMSE against the reference on the same per-path random streams: a central tile, 8 samples per pixel
+                try:
+                    import numpy as np
+                    tw = min(64, a.width); th = min(64, a.height)
+                    x0, y0 = (a.width - tw) // 2, (a.height - th) // 2
+                    prm8 = common.structs.RenderParams(a.width, a.height, 0, 8, a.depth, cfg.pixel_scheme, a.seed)
+                    ref_paths = arm.tile_paths(x0, y0, x0 + tw, y0 + th, 0, 8)
+                    gpu_paths = ctx.sample_paths(prm8, x0, y0, x0 + tw, y0 + th)
+                    ref_mean, gpu_mean = ref_paths.mean(axis=1), gpu_paths.astype(np.float64).mean(axis=1)
+                    rmse = float(np.sqrt(np.mean((gpu_mean - ref_mean) ** 2)))
+                    perr = common.path_errors(gpu_paths, ref_paths)
+                    line["image_rmse"] = {"value": rmse, "relative": rmse / float(np.abs(ref_mean).mean()),
+                                          "unit": "spectral radiance, RMSE over pixels and wavelengths of the 8-sample mean",
+                                          "tile": f"{tw}x{th} at the image centre, samples 0-7, {ref_paths.shape[0] * 8} paths",
+                                          "rng": "matched: both sides draw the same per-path Philox streams",
+                                          "paths_within_1e-3": float((perr <= 1e-3).mean()), "reference": arm.kind}
+                except Exception as exc:
+                    line["image_rmse"] = {"value": None, "error": repr(exc)}
                 arm.close()
                 line["cpu_baseline"] = {"value": paths / secs, "unit": "paths/s", "cores": arm.cores, "kind": arm.kind,
                                         "sample": f"{passes} full-frame passes of {a.width}x{a.height} at 1 sample per pixel ({paths} paths, {secs:.1f} s), "

@@ -363,6 +363,56 @@ extern "C" int drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, 
     return DRT_CUDA_OK;
 }
 
+/* record layout of a render with `max_depth` bounces (RenderLaunch in drt_device.cuh) */
+static void record_layout(const drt_cuda_context *ctx, uint32_t max_depth, RenderLaunch &L)
+{
+    L.eval_words = (uint32_t)ctx->eval_words;
+    const bool compact = ctx->all_fast && !ctx->f64_geometry;   /* the ALLFAST kernel and its compact records */
+    L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
+    if(L.bounce_words < 8) L.bounce_words = 8;
+    L.head_words = 4;
+    if(compact) { L.bounce_words = 4; L.head_words = (2 + (max_depth + 1) / 2 + 3u) & ~3u; }
+    L.path_words = L.head_words + max_depth * L.bounce_words;
+    L.path_stride = ((L.path_words / 4) & 1u) ? L.path_words : L.path_words + 4;
+}
+
+/* path records live in shared memory: use as many warps per CTA (the kernel's full count, then halves) as the record size
+ * allows, and as many CTAs per SM as shared memory and the register budget of the kernel's __launch_bounds__ allow */
+static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int *warps_out, int *ctas_out, size_t *smem_out)
+{
+    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, ctx->all_fast);
+    int warps = full_warps;
+    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots);
+    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); }
+    *warps_out = warps; *smem_out = smem;
+    if(smem > ctx->smem_optin) return false;
+    int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    int by_threads = (DRT_MIN_CTAS * full_warps) / warps;
+    if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if(ctas_per_sm < 1) ctas_per_sm = 1;
+    *ctas_out = ctas_per_sm;
+    return true;
+}
+
+extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_depth, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm)
+{
+    if(!ctx || max_depth == 0) return fail(DRT_CUDA_E_ARG, "bad argument");
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    RenderLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.pool_words = ctx->pool_words;
+    record_layout(ctx, max_depth, L);
+    int warps = 0, ctas = 0;
+    size_t smem = 0;
+    if(!launch_shape(ctx, L, &warps, &ctas, &smem)) return fail(DRT_CUDA_E_UNSUPPORTED, "records of max_cast_depth %u do not fit in shared memory", max_depth);
+    if(name && name_len)
+        snprintf(name, name_len, "drt::render_kernel<%s,%d,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
+                 (ctx->all_fast && !ctx->f64_geometry) ? "true" : "false");
+    if(warps_per_cta) *warps_per_cta = warps;
+    if(ctas_per_sm) *ctas_per_sm = ctas;
+    return DRT_CUDA_OK;
+}
+
 static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
                   FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr)
 {
@@ -381,30 +431,13 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
     uint32_t spp = p->sample_end - p->sample_begin;
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
-    L.eval_words = (uint32_t)ctx->eval_words;
-    const bool compact = ctx->all_fast && !ctx->f64_geometry;   /* the ALLFAST kernel and its compact records */
-    L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
-    if(L.bounce_words < 8) L.bounce_words = 8;
-    L.head_words = 4;
-    if(compact) { L.bounce_words = 4; L.head_words = (2 + (p->max_depth + 1) / 2 + 3u) & ~3u; }
-    L.path_words = L.head_words + p->max_depth * L.bounce_words;
-    L.path_stride = ((L.path_words / 4) & 1u) ? L.path_words : L.path_words + 4;
+    record_layout(ctx, p->max_depth, L);
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
-    /* path records live in shared memory: use as many warps per CTA (8, 4, 2, 1) as the record size allows */
-    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, ctx->all_fast);
-    int warps = full_warps;
-    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots);
-    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); }
-    if(smem > ctx->smem_optin)
+    int warps, ctas_per_sm;
+    size_t smem;
+    if(!launch_shape(ctx, L, &warps, &ctas_per_sm, &smem))
         return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
                     p->max_depth, ctx->nlights, smem, ctx->smem_optin);
-    int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-#ifndef DRT_MIN_CTAS
-#define DRT_MIN_CTAS 2
-#endif
-    int by_threads = (DRT_MIN_CTAS * full_warps) / warps;    /* register budget of the kernel's __launch_bounds__ */
-    if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
-    if(ctas_per_sm < 1) ctas_per_sm = 1;
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
     uint64_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;

@@ -20,6 +20,9 @@
 #define DRT_CTA_WARPS 8      /* warps per CTA of the general kernel */
 #endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
+#ifndef DRT_MIN_CTAS
+#define DRT_MIN_CTAS 2        /* resident CTAs per SM the render kernels are compiled for (__launch_bounds__) */
+#endif
 
 /* Spectral basis a BSDF evaluation is expressed in (eval_weights in drt_kernels.cu).  A material's lobe list fixes
  * which of the seven can ever be non-zero (bmask); only those weights are stored in a path record, in this order,

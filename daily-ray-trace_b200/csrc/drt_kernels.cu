@@ -605,9 +605,6 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 
 /* ------------------------------------------------------------------ path records in shared memory */
 
-#ifndef DRT_MIN_CTAS
-#define DRT_MIN_CTAS 2
-#endif
 #define REC_NB   0
 #define REC_VIG  1
 #define REC_HDR16 2   /* ALLFAST records: 16-bit bounce headers from word 2 */

@@ -14,7 +14,7 @@ GEOMETRY_F32, GEOMETRY_F64 = 0, 1
 
 EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
            "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
-           "drt_cuda_get_stats", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
+           "drt_cuda_get_stats", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
            "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close"]
@@ -58,6 +58,7 @@ def lib():
         L.drt_cuda_destroy.restype = None
         L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
         L.drt_cuda_scene_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        L.drt_cuda_render_kernel_info.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
         L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
@@ -122,6 +123,13 @@ class Context:
         v = C.c_size_t()
         _check(lib().drt_cuda_scene_upload_bytes(self._h, C.byref(v)))
         return v.value
+
+    def render_kernel_info(self, max_depth=4):
+        """(kernel name, warps per CTA, CTAs per SM) the uploaded scene and geometry precision select."""
+        name = C.create_string_buffer(96)
+        warps, ctas = C.c_int(), C.c_int()
+        _check(lib().drt_cuda_render_kernel_info(self._h, max_depth, name, len(name), C.byref(warps), C.byref(ctas)))
+        return name.value.decode(), warps.value, ctas.value
 
     def set_geometry_precision(self, precision):
         _check(lib().drt_cuda_set_geometry_precision(self._h, precision))
