@@ -19,6 +19,9 @@
 #ifndef DRT_CTA_WARPS
 #define DRT_CTA_WARPS 8      /* warps per CTA of the general kernel */
 #endif
+#ifndef DRT_FAST_WARPS
+#define DRT_FAST_WARPS 16     /* warps per CTA of the ALLFAST kernel: 2 CTAs x 16 warps x 64 registers fill an SM (measured: 8 -> 16 warps = +21 % paths/s) */
+#endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS
 #define DRT_MIN_CTAS 2        /* resident CTAs per SM the render kernels are compiled for (__launch_bounds__) */
