@@ -75,10 +75,23 @@ template <> struct Num<double>
     static __device__ __forceinline__ double unit(uint32_t r31) { return (double)r31 / 2147483647.0; }
 };
 
-template <typename R> __device__ __forceinline__ V3<R> normalise(V3<R> v)
+/* a / b and 1 / sqrt(x) for operands known to be in range: f32 uses the bare MUFU.RCP / MUFU.RSQ (<= 1-2 ulp) instead of the
+ * range-scaled sequences the compiler emits for '/' and sqrtf even under -prec-div=false (8-13 instructions per site) */
+__device__ __forceinline__ float  r_div(float a, float b)   { return a * r_rcp_fast(b); }
+__device__ __forceinline__ double r_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float  r_rsqrt(float x)  { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double r_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+template <typename R> __device__ __forceinline__ V3<R> normalise(V3<R> v);
+template <> __device__ __forceinline__ V3<double> normalise<double>(V3<double> v)   /* geometry.c: v / |v| */
 {
-    R len = r_sqrt(dot(v, v));
-    return mk<R>(v.x / len, v.y / len, v.z / len);
+    double len = sqrt(dot(v, v));
+    return mk<double>(v.x / len, v.y / len, v.z / len);
+}
+template <> __device__ __forceinline__ V3<float> normalise<float>(V3<float> v)
+{
+    float inv = r_rsqrt(dot(v, v));
+    return mk<float>(v.x * inv, v.y * inv, v.z * inv);
 }
 template <typename R> __device__ __forceinline__ V3<R> reflect(V3<R> v, V3<R> n)   /* geometry.c:85-90 */
 {
@@ -105,7 +118,7 @@ template <typename R> __device__ __forceinline__ V3<R> rotate_from_z(V3<R> n, V3
     if(dot(a, a) == R(0) && c <= R(0)) return neg(q);
     V3<R> aq = cross(a, q);
     V3<R> aaq = cross(a, aq);
-    R f = R(1) / (R(1) + c);
+    R f = r_div(R(1), R(1) + c);
     return (q + aq) + aaq * f;
 }
 
@@ -317,9 +330,9 @@ template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R>
 }
 
 /* points_mutually_visible, daily_ray_trace.c:238-270 */
-template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g, V3<R> p0, V3<R> p1, int skip)
+template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g, V3<R> p0, V3<R> p1, int skip, V3<R> &dir)
 {
-    V3<R> dir = normalise(p1 - p0);
+    dir = normalise(p1 - p0);   /* also the direction to the light of direct_light_contribution :318 */
     V3<R> o = p0 + dir * Num<R>::fudge();
     V3<R> po = p1 - o;
     R vis_dist = r_sqrt(dot(po, po)) - Num<R>::fudge();
@@ -473,8 +486,8 @@ template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /
     R ox = R(2) * rx - R(1), oy = R(2) * ry - R(1);
     if(ox == R(0) && oy == R(0)) return mk<R>(R(0), R(0), R(0));
     R r, t;   /* t in units of pi */
-    if(r_abs(ox) > r_abs(oy)) { r = ox; t = R(0.25) * (oy / ox); }
-    else                      { r = oy; t = R(0.5) - R(0.25) * (ox / oy); }
+    if(r_abs(ox) > r_abs(oy)) { r = ox; t = R(0.25) * r_div(oy, ox); }
+    else                      { r = oy; t = R(0.5) - R(0.25) * r_div(ox, oy); }
     R s, c;
     r_sincospi(t, &s, &c);
     return mk<R>(r * c, r * s, R(0));
@@ -597,7 +610,7 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
         }
         q.z = r_sqrt(R(1) - dot(q, q));
         in = rotate_from_z<R>(h.nrm, q);
-        inv_pdf = Num<R>::pi() / dot(h.nrm, in);
+        inv_pdf = r_div(Num<R>::pi(), dot(h.nrm, in));
         match = 0;
         return;
     }
@@ -722,10 +735,10 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                 k = g.light_pdf[ls];
             }
             shadow += 1;
-            if(visible<R>(g, h.pos, lp, h.plane_slot))
+            V3<R> ldir;
+            if(visible<R>(g, h.pos, lp, h.plane_slot, ldir))
             {
                 const uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
-                const V3<R> ldir = normalise(lp - h.pos);
                 if(plastic)
                 {
                     plastic_weights<R>(g, sm, h.nrm, h.out, ldir, fast ? (float)k : 1.f, wd_n, wg_n);
