@@ -79,6 +79,8 @@ template <> struct Num<double>
  * range-scaled sequences the compiler emits for '/' and sqrtf even under -prec-div=false (8-13 instructions per site) */
 __device__ __forceinline__ float  r_div(float a, float b)   { return a * r_rcp_fast(b); }
 __device__ __forceinline__ double r_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float  r_sqrt_fast(float x)  { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   /* MUFU.SQRT */
+__device__ __forceinline__ double r_sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float  r_rsqrt(float x)  { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ double r_rsqrt(double x) { return 1.0 / sqrt(x); }
 
@@ -447,13 +449,13 @@ __device__ __forceinline__ void plastic_weights(const GeomT<R> &g, int m, V3<R> 
 template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr, T inc_cos)
 {
     T inc_sin_sq = T(1) - inc_cos * inc_cos;
-    T rel = ir / tr;
+    T rel = r_div(ir, tr);
     T ts_sin_sq = rel * rel * inc_sin_sq;
     if(ts_sin_sq >= T(1)) return T(1);
-    T ts_cos = sqrt(T(1) - ts_sin_sq * ts_sin_sq);
+    T ts_cos = r_sqrt_fast(T(1) - ts_sin_sq * ts_sin_sq);
     T tr_on = tr * inc_cos, tr_ts = tr * ts_cos, ir_on = ir * inc_cos, ir_ts = ir * ts_cos;
-    T par = (tr_on - ir_ts) / (tr_on + ir_ts);
-    T per = (ir_on - tr_ts) / (ir_on + tr_ts);
+    T par = r_div(tr_on - ir_ts, tr_on + ir_ts);
+    T per = r_div(ir_on - tr_ts, ir_on + tr_ts);
     return T(0.5) * (par * par + per * per);
 }
 
@@ -461,19 +463,20 @@ template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr
 __device__ __forceinline__ float fresnel_conductor(float ir, float tr, float te, float inc_cos)
 {
     float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
-    float eta = tr / ir, kap = te / ir;
+    float inv_ir = r_rcp_fast(ir);
+    float eta = tr * inv_ir, kap = te * inv_ir;
     float eta_sq = eta * eta, kap_sq = kap * kap;
     float r = eta_sq - kap_sq - sin_sq;
-    float apb_sq = sqrtf(r * r + 4.f * eta_sq * kap_sq);
+    float apb_sq = r_sqrt_fast(r * r + 4.f * eta_sq * kap_sq);
     /* with kappa = 0 this is sqrt(|r| + r): exactly 0 for r < 0 in IEEE arithmetic (sqrt(r*r) == |r|), but the approximate
      * square root of the fast-math build may land one ulp low -> clamp instead of producing a NaN wavelength */
-    float a = sqrtf(fmaxf(0.5f * (apb_sq + r), 0.f));
+    float a = r_sqrt_fast(fmaxf(0.5f * (apb_sq + r), 0.f));
     float s = apb_sq + cos_sq;
     float t = 2.f * a * inc_cos;
     float u = cos_sq * apb_sq + sin_sq * sin_sq;
     float v = t * sin_sq;
-    float par = (s - t) / (s + t);
-    float per = par * (u - v) / (u + v);
+    float par = r_div(s - t, s + t);
+    float per = r_div(par * (u - v), u + v);
     return 0.5f * (par + per);
 }
 
