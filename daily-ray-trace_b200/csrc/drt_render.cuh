@@ -675,7 +675,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     }
     rec[REC_VIG] = (float)dot(d, fwd);   /* Q20 */
 
-    uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth, general = 0;
+    uint32_t nb = 0, closest = 0, shadow = 0, shaded = 0, end_depth = L.max_depth, general = 0, emitter = 0;
     int skip = -1;
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
     for(uint32_t depth = 0; depth < L.max_depth; depth += 1)
@@ -690,9 +690,8 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         {
             if(flags & 2)
             {
-                if(ALLFAST) reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)(KIND_EMIT | ((uint32_t)m << 2));
-                else rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3));   /* Q6 */
-                nb += 1;
+                if(ALLFAST) emitter = (uint32_t)(m + 1) << 16;   /* compact records: the closing emitter rides in word 0 */
+                else { rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3)); nb += 1; }   /* Q6 */
             }
             end_depth = depth;
             break;
@@ -763,7 +762,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         {
             /* compact record: four weights per bounce, the 16-bit header (kind | plastic block word offset, a multiple of 4) apart */
             *reinterpret_cast<float4 *>(rec + L.head_words + 4u * nb) = make_float4(wd_n, wg_n, wd_s, wg_s);
-            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)(KIND_SHADE | (uint32_t)ix.plastic[sm]);
+            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)ix.plastic[sm];
         }
         else if(fast)
         {
@@ -784,7 +783,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         o = h.pos;
         skip = h.plane_slot;
     }
-    rec[REC_NB] = __uint_as_float(nb);
+    rec[REC_NB] = __uint_as_float(nb | emitter);
     tally[0] += closest; tally[1] += shadow; tally[2] += shaded; tally[3] += rng.draws;
     /* bits 0-7: histogram bin (depth of termination, 8 = hit the cap); bit 8: the record has a bounce that needs the general shader */
     return ((end_depth < L.max_depth) ? (end_depth < 7 ? end_depth : 7) : 8) | (general << 8);
@@ -799,6 +798,11 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
 { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+/* acc += a * b and x *= t in place: the loop-carried accumulators keep their registers */
+__device__ __forceinline__ void fma2_acc(unsigned long long &acc, unsigned long long a, unsigned long long b)
+{ asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void mul2_by(unsigned long long &x, unsigned long long t)
+{ asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(t)); }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
 { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
@@ -954,28 +958,22 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
         /* compact records (RenderLaunch in drt_device.cuh): header halves from word 2, four weights per bounce */
         const uint16_t *hp = reinterpret_cast<const uint16_t *>(col + REC_HDR16);
         const float4 *wp = reinterpret_cast<const float4 *>(col + L.head_words);
-        for(uint32_t b = 0; b < nb; b += 1)
+        const uint32_t nshade = nb & 0xffffu;
+#pragma unroll 1
+        for(uint32_t b = 0; b < nshade; b += 1)
         {
             const uint32_t hdr = hp[b];
-            if((hdr & 3u) != KIND_SHADE)   /* the path ran into an emitter, cast_ray :453-457 */
-            {
-                const float *row = pool_lane + ix.row[hdr >> 2][DRT_SPD_EMISSION];
-#pragma unroll
-                for(int k = 0; k < NP; k += 1) dst2[k] = fma2(thr2[k], pk2(row[(2 * k) * DRT_HALF], row[(2 * k + 1) * DRT_HALF]), dst2[k]);
-                if(NS & 1) dst1 = fmaf(thr1, row[(NS - 1) * DRT_HALF], dst1);
-                break;
-            }
             const float4 w = wp[b];   /* wd_n k, wg_n k, wd_s / pdf, wg_s / pdf */
-            const float4 *blk = reinterpret_cast<const float4 *>(pool + (hdr & 0xfffcu)) + lane16;
+            const float4 *blk = reinterpret_cast<const float4 *>(pool + hdr) + lane16;
             const unsigned long long wdn = pk2(w.x, w.x), wgn = pk2(w.y, w.y), wds = pk2(w.z, w.z), wgs = pk2(w.w, w.w);
 #pragma unroll
             for(int k = 0; k < NP; k += 1)
             {
                 const float4 dg = blk[(2 * k) * DRT_HALF], ee = blk[(2 * k + 1) * DRT_HALF];
                 unsigned long long f = fma2(wgn, pk2(ee.z, ee.w), mul2(wdn, pk2(ee.x, ee.y)));
-                dst2[k] = fma2(thr2[k], f, dst2[k]);
+                fma2_acc(dst2[k], thr2[k], f);
                 unsigned long long t = fma2(wgs, pk2(dg.z, dg.w), mul2(wds, pk2(dg.x, dg.y)));
-                thr2[k] = mul2(thr2[k], t);
+                mul2_by(thr2[k], t);
             }
             if(NS & 1)
             {
@@ -983,6 +981,13 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
                 dst1 = fmaf(thr1, fmaf(w.y, q.w, w.x * q.z), dst1);
                 thr1 *= fmaf(w.w, q.y, w.z * q.x);
             }
+        }
+        if(nb >> 16)   /* the path ran into an emitter, cast_ray :453-457 */
+        {
+            const float *row = pool_lane + ix.row[(nb >> 16) - 1u][DRT_SPD_EMISSION];
+#pragma unroll
+            for(int k = 0; k < NP; k += 1) fma2_acc(dst2[k], thr2[k], pk2(row[(2 * k) * DRT_HALF], row[(2 * k + 1) * DRT_HALF]));
+            if(NS & 1) dst1 = fmaf(thr1, row[(NS - 1) * DRT_HALF], dst1);
         }
     }
     else
@@ -1287,7 +1292,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
              * cost: paths without any bounce record first, then plastic-only paths by bounce count, then paths that need the
              * general shader by bounce count; idle lanes last.  A 32-wide bitonic sort over (key, lane).  The film is a
              * sum / Welford accumulation, so the order only changes rounding. */
-            const uint32_t cls = (my_nb == 0u) ? 0u : min(my_nb, 15u) + (general ? 16u : 0u);
+            const uint32_t cls = (my_nb == 0u) ? 0u : min((my_nb & 0xffffu) + (my_nb >> 16 ? 1u : 0u), 15u) + (general ? 16u : 0u);
             uint32_t v = (lane >= count) ? 0xffffffffu : (((my_px << 5) | cls) << 5) | lane;
 #pragma unroll
             for(uint32_t k = 2; k <= 32; k <<= 1)
