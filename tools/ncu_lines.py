@@ -56,24 +56,24 @@ print(f"total {tot / paths:.1f} warp-instr/path, {len(data)} SASS instructions")
 for (f, ln), (ex, sm, thr, cnt) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
     text = text_of(f, ln)
     print(f"{f[:14]:14s}{ln:5d} {ex / paths:6.2f}/path {100 * ex / tot:5.1f}% smp {100 * sm / totS:5.1f}% thr {thr / max(ex, 1):4.1f} sass {cnt:4d} | {text}")
-# regions of drt_kernels.cu, found by their section markers so that the table follows the source
+# regions of drt_render.cuh, found by their section markers so that the table follows the source
 MARKS = [("small vector algebra", "vector algebra (inlined)"), ("per-path random stream", "rng"), ("K2: closest hit", "nearest_surface / hit_*"),
          ("template <typename R> struct Hit", "closest_hit / visible"), ("BSDF evaluation reduced to basis weights", "eval weights"),
          ("dielectric Fresnel at one wavelength", "fresnel"), ("K4: the six direction samplers", "samplers"),
          ("path records in shared memory", "trace_path"), ("packed f32x2 arithmetic", "packed ops"),
          ("phase 2: spectral replay", "replay"), ("film of one pixel held by a half warp", "film"), ("the kernel */", "kernel body")]
-text_of("drt_kernels.cu", 1)
+text_of("drt_render.cuh", 1)
 RANGES = []
 for key, name in MARKS:
-    at = next((i + 1 for i, l in enumerate(srcs["drt_kernels.cu"]) if key in l), None)
+    at = next((i + 1 for i, l in enumerate(srcs["drt_render.cuh"]) if key in l), None)
     if at: RANGES.append([at, 10**9, name])
 RANGES.sort()
 for i in range(len(RANGES) - 1): RANGES[i][1] = RANGES[i + 1][0] - 1
 for (f, ln), (ex, sm, thr, cnt) in per_line.items():
     name = f
-    if f == "drt_kernels.cu":
+    if f == "drt_render.cuh":
         name = next((n for a, b, n in RANGES if a <= ln <= b), "other")
     groups[name] += ex
-print("--- by region (line ranges of drt_kernels.cu as of the capture; other files by name)")
+print("--- by region (line ranges of drt_render.cuh as of the capture; other files by name)")
 for name, ex in sorted(groups.items(), key=lambda kv: -kv[1]):
     print(f"  {ex / paths:7.2f}/path {100 * ex / tot:5.1f}%  {name}")
