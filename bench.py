@@ -49,8 +49,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--geometry", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU film combination: fused peer-memory kernel (CUDA IPC over NVLink) or NCCL collectives")
+    ap.add_argument("--merge", default="scatter", choices=["scatter", "p2p", "nccl"],
+                    help="multi-GPU film combination: render kernel scatters finished pixels to their owner over NVLink + local merge "
+                         "(default), gather-merge kernel over peer memory, or NCCL collectives")
     return ap.parse_args()
 
 
@@ -265,10 +266,12 @@ def run_b200_arm(a):
     ctx.set_geometry_precision(cuda.GEOMETRY_F64 if a.geometry == "f64" else cuda.GEOMETRY_F32)
     dev = torch.device("cuda", local)
     peers, merge_kind = None, "none"
-    if world > 1 and a.merge == "p2p":
+    if world > 1 and a.merge in ("scatter", "p2p"):
         try:
-            peers = film_mod.PeerFilmGroup(ctx, a.width, a.height)
-            merge_kind = "p2p: one fused merge+images kernel per rank over CUDA-IPC peer memory"
+            peers = film_mod.PeerFilmGroup(ctx, a.width, a.height, scatter=a.merge == "scatter")
+            merge_kind = ("scatter: the render kernel stores each finished pixel into its owner's staging film over NVLink (CUDA IPC), "
+                          "then one local merge+images kernel per rank") if a.merge == "scatter" else \
+                         "p2p: one fused gather-merge+images kernel per rank over CUDA-IPC peer memory"
         except Exception as exc:
             print(f"[rank {rank}] peer-memory merge unavailable ({exc}); using NCCL", file=sys.stderr)
             peers = None
@@ -303,8 +306,14 @@ def run_b200_arm(a):
     prm = common.structs.RenderParams(a.width, a.height, rank * a.spp, (rank + 1) * a.spp, a.depth, cfg.pixel_scheme, a.seed)
     paths_per_step = a.width * a.height * a.spp * world
 
+    def render():
+        if peers is not None:
+            peers.render(prm, stream.cuda_stream)
+        else:
+            ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
+
     def step():
-        ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
+        render()
         return combine()
 
     def fence():
@@ -326,7 +335,7 @@ def run_b200_arm(a):
     e0.record(stream)
     for i in range(a.steps):
         k_start[i].record(stream)
-        ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
+        render()
         k_stop[i].record(stream)
         combine()
         launches += 1 + (1 if peers is not None else 0)
@@ -352,7 +361,7 @@ def run_b200_arm(a):
         if world == 1:
             ctx.render_host_into(prm, host_film)           # the C-ABI host-buffer call of include/drt_cuda.h
         else:
-            ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
+            render()
             combine()
             if rank == 0:
                 for k in ("sum", "filter", "mean", "m2"):

@@ -22,7 +22,7 @@ void        drt_launch_film_to_rgb(const void *tables, const float *plane, const
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
 void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
 void        drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream_t stream);
-void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end,
+void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end, uint32_t src_base,
                                          uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream);
 size_t      drt_rgb_tables_bytes(void);
 void        drt_fill_rgb_tables(void *dst_host, const drt_tables *t);
@@ -414,7 +414,8 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_d
 }
 
 static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
-                  FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr)
+                  FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr,
+                  const drt_film *scatter = nullptr, int scatter_count = 0, int scatter_rank = 0, uint64_t scatter_slice = 0)
 {
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
@@ -431,6 +432,8 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
     uint32_t spp = p->sample_end - p->sample_begin;
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
+    for(int i = 0; i < scatter_count; i += 1) L.scatter[i] = FilmPtrs{ scatter[i].sum, scatter[i].filter, scatter[i].mean, scatter[i].m2 };
+    L.scatter_count = (uint32_t)scatter_count; L.scatter_rank = (uint32_t)scatter_rank; L.scatter_slice = (uint32_t)scatter_slice;
     record_layout(ctx, p->max_depth, L);
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     int warps, ctas_per_sm;
@@ -457,6 +460,18 @@ extern "C" int drt_cuda_render_device(drt_cuda_context *ctx, const drt_render_pa
     if(!ctx || !params || !film || !film->sum || !film->filter || !film->mean || !film->m2) return fail(DRT_CUDA_E_ARG, "NULL argument");
     FilmPtrs f = { film->sum, film->filter, film->mean, film->m2 };
     return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *staging, int count, int rank,
+                                              uint64_t slice_pixels, void *stream)
+{
+    if(!ctx || !params || !staging || count < 1 || count > DRT_MAX_PEERS || rank < 0 || rank >= count) return fail(DRT_CUDA_E_ARG, "bad argument (1..%d staging films)", DRT_MAX_PEERS);
+    uint64_t npix = (uint64_t)params->width * params->height;
+    if(slice_pixels == 0 || slice_pixels * (uint64_t)count < npix || slice_pixels > 0xffffffffull) return fail(DRT_CUDA_E_ARG, "slices of %llu pixels do not cover the image", (unsigned long long)slice_pixels);
+    for(int i = 0; i < count; i += 1)
+        if(!staging[i].sum || !staging[i].filter || !staging[i].mean || !staging[i].m2) return fail(DRT_CUDA_E_ARG, "NULL staging film %d", i);
+    FilmPtrs f = { staging[0].sum, staging[0].filter, staging[0].mean, staging[0].m2 };
+    return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, (cudaStream_t)stream, nullptr, nullptr, staging, count, rank, slice_pixels);
 }
 
 static int ensure(float **buf, size_t *have, size_t need)
@@ -689,8 +704,34 @@ extern "C" int drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *d
     FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 };
     if(pixel_end > pixel_begin)
     {
-        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, bgra_sum, bgra_mean, bgra_var,
+        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, 0u, bgra_sum, bgra_mean, bgra_var,
                                      ctx->num_sms * 8, (cudaStream_t)stream);
+        CU(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film *dst, const drt_film *staging, int count, uint64_t slice_pixels,
+                                          uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
+                                          uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream)
+{
+    if(!ctx || !dst || !staging || count < 1 || count > DRT_MAX_PEERS) return fail(DRT_CUDA_E_ARG, "bad argument (1..%d ranks)", DRT_MAX_PEERS);
+    if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
+    uint64_t npix = (uint64_t)width * height;
+    if(pixel_begin > pixel_end || pixel_end > npix || pixel_end - pixel_begin > slice_pixels) return fail(DRT_CUDA_E_ARG, "bad pixel range");
+    if((bgra_sum || bgra_mean || bgra_var) && !(bgra_sum && bgra_mean && bgra_var)) return fail(DRT_CUDA_E_ARG, "give all three image buffers or none");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n;
+    FilmPtrs films[DRT_MAX_PEERS];
+    for(int g = 0; g < count; g += 1)   /* rank g's partial film of this slice: staging pixels [g * slice, (g + 1) * slice) */
+        films[g] = FilmPtrs{ staging->sum + (size_t)g * slice_pixels * n, staging->filter + (size_t)g * slice_pixels,
+                             staging->mean + (size_t)g * slice_pixels * n, staging->m2 + (size_t)g * slice_pixels * n };
+    FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 };
+    if(pixel_end > pixel_begin)
+    {
+        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, (uint32_t)pixel_begin,
+                                     bgra_sum, bgra_mean, bgra_var, ctx->num_sms * 8, (cudaStream_t)stream);
         CU(cudaGetLastError());
         ctx->launches += 1;
     }

@@ -91,6 +91,7 @@ struct SpdIndex
 };
 
 struct FilmPtrs { float *sum, *filter, *mean, *m2; };
+#define DRT_MAX_PEERS 16
 
 struct DeviceStats
 {
@@ -143,4 +144,10 @@ struct RenderLaunch
     uint32_t path_words;           /* head_words + max_depth*bounce_words */
     uint32_t path_stride;          /* words between the records of consecutive slots: >= path_words, 4 * odd */
     uint32_t geom_bytes, pool_words;
+    /* scattered film store (multi-GPU, drt_cuda_render_device_scatter): pixel p belongs to rank p / scatter_slice, and this
+     * rank's partial film of it is written -- over NVLink when the owner is a peer -- into the owner's staging film at pixel
+     * scatter_rank * scatter_slice + p % scatter_slice, so every owner ends up with all ranks' partial films of its slice in
+     * local memory.  scatter_count = 0: plain store to `film`. */
+    uint32_t scatter_count, scatter_rank, scatter_slice, scatter_pad;
+    FilmPtrs scatter[DRT_MAX_PEERS];
 };

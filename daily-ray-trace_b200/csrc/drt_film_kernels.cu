@@ -131,7 +131,7 @@ struct FilmSet { int count; FilmPtrs film[16]; };
 
 template <int CHUNK>
 __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables *tables, FilmSet set, FilmPtrs dst, uint32_t pixel_begin,
-                                                                uint32_t pixel_end, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
+                                                                uint32_t pixel_end, uint32_t src_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
 {
     __shared__ RgbTables t;
     for(uint32_t i = threadIdx.x; i < sizeof(RgbTables) / 4; i += blockDim.x)
@@ -154,12 +154,12 @@ __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables 
             {
                 const bool on = g0 + c < set.count;
                 const FilmPtrs &f = set.film[on ? g0 + c : g0];
-                nb[c] = on ? f.filter[p] : 0.f;
+                nb[c] = on ? f.filter[p - src_base] : 0.f;
 #pragma unroll
                 for(int k = 0; k < DRT_MAX_SLOTS; k += 1)
                 {
                     uint32_t wl = lane + k * 32;
-                    size_t at = (size_t)p * n + wl;
+                    size_t at = (size_t)(p - src_base) * n + wl;   /* sources are indexed from src_base (0 for whole films, the slice start for staged slices) */
                     bool ld = on && wl < n;
                     rs[c][k] = ld ? f.sum[at] : 0.f; rm[c][k] = ld ? f.mean[at] : 0.f; rv[c][k] = ld ? f.m2[at] : 0.f;
                 }
@@ -289,16 +289,16 @@ void drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream
 }
 
 void drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end,
-                                  uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream)
+                                  uint32_t src_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream)
 {
     drt::FilmSet set;
     set.count = count;
     for(int i = 0; i < count && i < 16; i += 1) set.film[i] = films[i];
     if(count <= 2)
-        drt::film_gather_merge_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
+        drt::film_gather_merge_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base,
                                                                   bgra_sum, bgra_mean, bgra_var);
     else
-        drt::film_gather_merge_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end,
+        drt::film_gather_merge_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base,
                                                                   bgra_sum, bgra_mean, bgra_var);
 }
 

@@ -1236,6 +1236,19 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
      * 32 paths) or 32/spp whole pixels traced as ONE batch.  Either way phase 2 walks the batch pixel by pixel, both half
      * warps shading samples of the same pixel, two paths at a time. */
     constexpr bool paired = PAIRED;
+    /* the pixel's finished film goes to `film`, or (multi-GPU scatter) to the staging film of the rank that owns the pixel */
+    auto store_pixel = [&](uint32_t gpix, const PixelFilm<NS> &f)
+    {
+        FilmPtrs out = L.film;
+        uint32_t at = gpix;
+        if(L.scatter_count)
+        {
+            const uint32_t owner = gpix / L.scatter_slice;
+            out = L.scatter[owner];
+            at = L.scatter_rank * L.scatter_slice + (gpix - owner * L.scatter_slice);
+        }
+        film_store<NS>(out, at, n, lane, f);
+    };
     const bool dumping = L.path_dump || L.record_dump;
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
@@ -1342,7 +1355,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
                 if(!paired)
                 {
                     film.merge_halves();
-                    if(have_film) film_store<NS>(L.film, gpix, n, lane, film);
+                    if(have_film) store_pixel(gpix, film);
                 }
             }
             __syncwarp();
@@ -1350,7 +1363,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
         if(paired)
         {
             film.merge_halves();
-            if(have_film) film_store<NS>(L.film, task_y * L.width + task_x, n, lane, film);
+            if(have_film) store_pixel(task_y * L.width + task_x, film);
         }
     }
 

@@ -16,7 +16,7 @@ EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "d
            "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
            "drt_cuda_get_stats", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
-           "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
+           "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
            "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close"]
 
 
@@ -62,6 +62,9 @@ def lib():
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
         L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
+        L.drt_cuda_render_device_scatter.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        L.drt_cuda_film_merge_slices.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                 C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.drt_cuda_render_host.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film)]
         L.drt_cuda_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.drt_cuda_sample_paths.argtypes = [C.c_void_p, C.POINTER(RenderParams)] + [C.c_uint32] * 4 + [C.c_void_p]
@@ -224,6 +227,15 @@ class Context:
         b = bgra or (None, None, None)
         _check(lib().drt_cuda_film_merge_many(self._h, C.byref(dst), arr, len(srcs), width, height, pixel_begin, pixel_end,
                                               b[0], b[1], b[2], stream))
+
+    def render_device_scatter(self, params, staging, rank, slice_pixels, stream=None):
+        arr = (Film * len(staging))(*staging)
+        _check(lib().drt_cuda_render_device_scatter(self._h, C.byref(params), arr, len(staging), rank, slice_pixels, stream))
+
+    def film_merge_slices(self, dst, staging, count, slice_pixels, width, height, pixel_begin, pixel_end, bgra=None, stream=None):
+        b = bgra or (None, None, None)
+        _check(lib().drt_cuda_film_merge_slices(self._h, C.byref(dst), C.byref(staging), count, slice_pixels, width, height,
+                                                pixel_begin, pixel_end, b[0], b[1], b[2], stream))
 
     def measure_fp32_peak(self, packed=False):
         v = C.c_double()

@@ -64,17 +64,24 @@ def merge_distributed_(film, root=0, group=None):
 
 
 class PeerFilmGroup:
-    """The fused multi-GPU epilogue over peer memory (drt_cuda_film_merge_many): every rank owns a library-allocated partial
-    film; all partial films, the root's merged film and the root's three BGRA images are mapped into every process through
-    CUDA IPC once, then each step every rank runs ONE kernel over its pixel slice that reads all partial films over
-    NVLink, merges them exactly and writes merged planes + images straight into the root's memory.
-    torch.distributed is used only to exchange the 64-byte handles and for the two host barriers around the kernel."""
+    """The fused multi-GPU film exchange over peer memory.  Every rank owns a library-allocated STAGING film; all staging films,
+    the root's merged film and the root's three BGRA images are mapped into every process through CUDA IPC once.
 
-    def __init__(self, ctx, width, height, root=0, group=None):
-        self.ctx, self.width, self.height, self.root, self.group = ctx, width, height, root, group
+    scatter=True (default): the render kernel itself does the scatter half -- each rank writes every finished pixel straight
+    into the staging film of the rank that owns the pixel's slice (drt_cuda_render_device_scatter: peer stores over NVLink
+    that hide under the render), then every rank merges the partial films of its slice from LOCAL memory and writes merged
+    planes + images into the root's memory (drt_cuda_film_merge_slices).
+    scatter=False: plain render into the local film, then one kernel per rank that reads all ranks' rows of its slice over
+    NVLink (drt_cuda_film_merge_many).
+    torch.distributed is used only to exchange the 64-byte handles and for the two host barriers around the merge kernel."""
+
+    def __init__(self, ctx, width, height, root=0, group=None, scatter=True):
+        self.ctx, self.width, self.height, self.root, self.group, self.scatter = ctx, width, height, root, group, scatter
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         npix = width * height
-        self.mine = ctx.film_alloc(width, height)
+        self.slice = -(-npix // self.world)                      # pixels per owner; staging holds world * slice pixels
+        rows = -(-self.slice * self.world // width) if scatter else height
+        self.mine = ctx.film_alloc(width, rows)
         self.merged = ctx.film_alloc(width, height) if self.rank == root else None
         self.images = ctx.buffer_alloc(3 * npix * 4) if self.rank == root else None
         handles = [None] * self.world
@@ -96,15 +103,29 @@ class PeerFilmGroup:
             self.dst = ctx.film_ipc_open(rooted[0][0])
             self._opened.append(self.dst)
             self.img_base = ctx.buffer_ipc_open(rooted[0][1])
-        self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
+        if scatter:
+            self.p0, self.p1 = min(npix, self.rank * self.slice), min(npix, (self.rank + 1) * self.slice)
+        else:
+            self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
         self.bgra = [self.img_base + i * npix * 4 for i in range(3)]
         dist.barrier(group=group)
+
+    def render(self, params, stream_ptr=None):
+        """This rank's samples of every pixel, into the exchange's staging memory."""
+        if self.scatter:
+            self.ctx.render_device_scatter(params, self.films, self.rank, self.slice, stream=stream_ptr)
+        else:
+            self.ctx.render_device(params, self.mine, accumulate=False, stream=stream_ptr)
 
     def merge(self, stream_ptr=None, sync=None):
         """Call after this rank's render was enqueued.  `sync` = callable that waits for this rank's stream."""
         sync()
-        dist.barrier(group=self.group)          # every rank's partial film is complete
-        self.ctx.film_merge_many(self.dst, self.films, self.width, self.height, self.p0, self.p1, bgra=self.bgra, stream=stream_ptr)
+        dist.barrier(group=self.group)          # every rank's partial film is complete (and, scattered, has arrived)
+        if self.scatter:
+            self.ctx.film_merge_slices(self.dst, self.mine, self.world, self.slice, self.width, self.height, self.p0, self.p1,
+                                       bgra=self.bgra, stream=stream_ptr)
+        else:
+            self.ctx.film_merge_many(self.dst, self.films, self.width, self.height, self.p0, self.p1, bgra=self.bgra, stream=stream_ptr)
         sync()
         dist.barrier(group=self.group)          # the root's merged film and images are complete
         return 1

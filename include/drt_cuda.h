@@ -84,6 +84,15 @@ int  drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, uint32_t h
 int  drt_cuda_render_device(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_device,
                             int accumulate, void *stream);
 
+/* Multi-GPU render fused with the scatter half of the film exchange.  The image's pixels are split into `count` slices of
+ * `slice_pixels` (rank r owns pixels [r * slice_pixels, (r + 1) * slice_pixels)); staging_device[o] is the staging film in the
+ * memory of rank o (local or a peer mapping from drt_cuda_film_ipc_open), sized for count * slice_pixels pixels.  This rank
+ * (`rank`) renders its samples of EVERY pixel and writes each finished pixel straight into its owner's staging film at pixel
+ * rank * slice_pixels + (p - owner * slice_pixels): peer stores over NVLink, issued as pixels finish, so the transfer hides
+ * under the render.  Afterwards every owner holds all ranks' partial films of its slice locally (drt_cuda_film_merge_slices). */
+int  drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *staging_device, int count, int rank,
+                                    uint64_t slice_pixels, void *stream);
+
 /* The same through HOST buffers: renders into library-owned device planes, then copies the four planes to
  * `film_host` (pinned or pageable) and waits.  This is the end-to-end call the Linux main uses. */
 int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_host);
@@ -143,6 +152,14 @@ int  drt_cuda_buffer_ipc_close(drt_cuda_context *ctx, void *mapped);
 int  drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *srcs_device, int count,
                               uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
                               uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
+
+/* The merge half of the scattered exchange, ONE kernel per rank on LOCAL data: merges the `count` partial films of this rank's
+ * slice [pixel_begin, pixel_end) held in staging_device (layout of drt_cuda_render_device_scatter), writes the merged planes
+ * to dst_device at the global pixel positions (may be peer memory, e.g. the root's film) and the three images like
+ * drt_cuda_film_merge_many. */
+int  drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *staging_device, int count, uint64_t slice_pixels,
+                                uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
+                                uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
 
 /* Measured FP32 FMA throughput of this device (TFLOP/s, FFMA counted as 2 flops): the roofline denominator
  * MEASURED_PEAKS.json does not carry.  packed=1 uses fma.rn.f32x2. */

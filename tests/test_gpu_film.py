@@ -172,6 +172,44 @@ def test_merge_many_fused_epilogue(ctx):
         ctx.film_free(f)
 
 
+@pytest.mark.parametrize("ranks,w,h", [(2, 40, 24), (3, 37, 23)])
+def test_scattered_render_and_slice_merge(ctx, ranks, w, h):
+    """The scattered exchange (multi-GPU default) emulated on one device: every "rank" renders its sample range of every pixel
+    with drt_cuda_render_device_scatter into the owners' staging films, every owner merges its slice with
+    drt_cuda_film_merge_slices -> the merged film equals the single render of all samples.  Ragged: 37*23 pixels over 3 ranks."""
+    import torch
+    depth, per = 4, 32
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, per * ranks, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    dev = torch.device("cuda", 0)
+    npix = w * h
+    whole = film_mod.FilmPlanes(w, h, n, dev)
+    ctx.render_device(oracledriver.params(w, h, 0, per * ranks, depth, cfg.pixel_scheme, 9), whole.as_drt_film())
+    slice_px = -(-npix // ranks)
+    rows = -(-slice_px * ranks // w)
+    staging = [ctx.film_alloc(w, rows) for _ in range(ranks)]          # staging[o]: all ranks' partial films of owner o's slice
+    for r in range(ranks):
+        ctx.render_device_scatter(oracledriver.params(w, h, r * per, (r + 1) * per, depth, cfg.pixel_scheme, 9), staging, r, slice_px)
+    merged = film_mod.FilmPlanes(w, h, n, dev)
+    imgs = [torch.zeros(npix, dtype=torch.int32, device=dev) for _ in range(3)]
+    for o in range(ranks):
+        p0, p1 = min(npix, o * slice_px), min(npix, (o + 1) * slice_px)
+        ctx.film_merge_slices(merged.as_drt_film(), staging[o], ranks, slice_px, w, h, p0, p1, bgra=[t.data_ptr() for t in imgs])
+    torch.cuda.synchronize()
+    assert torch.equal(merged.filter, whole.filter)
+    for name in ("sum", "mean", "m2"):
+        assert _rel(getattr(merged, name).cpu().numpy(), getattr(whole, name).cpu().numpy()).max() < 2e-4, name
+    ref_img = torch.zeros(npix, dtype=torch.int32, device=dev)
+    ctx.film_to_rgb(merged.as_drt_film(), w, h, 1, None, ref_img.data_ptr())
+    torch.cuda.synchronize()
+    a, b = imgs[1].cpu().numpy().view(np.uint32), ref_img.cpu().numpy().view(np.uint32)
+    assert max(np.abs(((a >> s) & 255).astype(int) - ((b >> s) & 255).astype(int)).max() for s in (0, 8, 16)) <= 1
+    for f in staging:
+        ctx.film_free(f)
+
+
 @pytest.mark.parametrize("scene", ["cornell_plane_light", "stress_all"])
 def test_large_render_is_finite(ctx, scene):
     """67 M paths through glass, gold and mirrors: no sample may poison a pixel with NaN/inf.  (Regression: with the
