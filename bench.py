@@ -342,6 +342,13 @@ def run_b200_arm(a):
     e1.record(stream)
     fence()
     t1 = time.perf_counter()
+    merge_ms = None
+    if peers is not None:      # one more (untimed) step with the exchange's phases timed on the host
+        peers.timing = []
+        step()
+        fence()
+        merge_ms = {k: 1e3 * v for k, v in zip(("wait_own_render", "barrier_before", "merge_kernel", "barrier_after"), peers.timing[-1])}
+        peers.timing = None
     ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -415,6 +422,7 @@ def run_b200_arm(a):
             "e2e": {"value": paths_per_step * a.steps / e2e_s, "unit": "paths/s", "h2d_bytes_per_step": upload_bytes,
                     "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches,
+            "film_exchange_ms": merge_ms,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (profiles/ncu_traffic.json); null for other image sizes",

@@ -443,6 +443,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
                     p->max_depth, ctx->nlights, smem, ctx->smem_optin);
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
     uint64_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+    if(scatter_count > 1) L.task_rotate = (uint32_t)((((uint64_t)scatter_rank * scatter_slice) / L.pixels_per_task) % ntasks);
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
     uint64_t need = (ntasks + warps - 1) / warps;
     if(grid > need) grid = need;

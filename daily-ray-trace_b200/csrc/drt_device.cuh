@@ -148,6 +148,8 @@ struct RenderLaunch
      * rank's partial film of it is written -- over NVLink when the owner is a peer -- into the owner's staging film at pixel
      * scatter_rank * scatter_slice + p % scatter_slice, so every owner ends up with all ranks' partial films of its slice in
      * local memory.  scatter_count = 0: plain store to `film`. */
-    uint32_t scatter_count, scatter_rank, scatter_slice, scatter_pad;
+    uint32_t scatter_count, scatter_rank, scatter_slice;
+    uint32_t task_rotate;          /* tasks are walked from this index (mod the task count): with scatter_rank * slice every rank starts in its own
+                                    * slice, so at any moment each owner receives from one peer instead of from all of them */
     FilmPtrs scatter[DRT_MAX_PEERS];
 };

@@ -1259,6 +1259,8 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
         if(lane == 0) task = atomicAdd(L.task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if(task >= ntasks) break;
+        task += L.task_rotate;
+        if(task >= ntasks) task -= ntasks;
         const uint32_t p_begin = task * L.pixels_per_task;
         const uint32_t p_end = min(p_begin + L.pixels_per_task, npix);
         const uint32_t total = (p_end - p_begin) * spp;

@@ -108,6 +108,7 @@ class PeerFilmGroup:
         else:
             self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
         self.bgra = [self.img_base + i * npix * 4 for i in range(3)]
+        self.timing = None
         dist.barrier(group=group)
 
     def render(self, params, stream_ptr=None):
@@ -118,16 +119,24 @@ class PeerFilmGroup:
             self.ctx.render_device(params, self.mine, accumulate=False, stream=stream_ptr)
 
     def merge(self, stream_ptr=None, sync=None):
-        """Call after this rank's render was enqueued.  `sync` = callable that waits for this rank's stream."""
+        """Call after this rank's render was enqueued.  `sync` = callable that waits for this rank's stream.
+        self.timing (if set to a list) receives (wait for own render, barrier, merge kernel, barrier) in seconds."""
+        import time
+        t0 = time.perf_counter()
         sync()
+        t1 = time.perf_counter()
         dist.barrier(group=self.group)          # every rank's partial film is complete (and, scattered, has arrived)
+        t2 = time.perf_counter()
         if self.scatter:
             self.ctx.film_merge_slices(self.dst, self.mine, self.world, self.slice, self.width, self.height, self.p0, self.p1,
                                        bgra=self.bgra, stream=stream_ptr)
         else:
             self.ctx.film_merge_many(self.dst, self.films, self.width, self.height, self.p0, self.p1, bgra=self.bgra, stream=stream_ptr)
         sync()
+        t3 = time.perf_counter()
         dist.barrier(group=self.group)          # the root's merged film and images are complete
+        if self.timing is not None:
+            self.timing.append((t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
         return 1
 
     def close(self):
