@@ -62,6 +62,9 @@ struct drt_cuda_context
     uint64_t launches = 0;
     size_t upload_bytes = 0;
     uint64_t last_launches = 0;
+    /* render_host pipelines the frame in row bands: render on one stream, read finished bands back on the other */
+    cudaStream_t band_render = nullptr, band_copy = nullptr;
+    cudaEvent_t  band_done[16] = {};
 };
 
 extern "C" const char *drt_cuda_last_error(void) { return g_err; }
@@ -98,6 +101,9 @@ extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
     cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats); cudaFree(ctx->d_counter); cudaFree(ctx->d_film); cudaFree(ctx->d_dump);
+    if(ctx->band_render) cudaStreamDestroy(ctx->band_render);
+    if(ctx->band_copy) cudaStreamDestroy(ctx->band_copy);
+    for(int i = 0; i < 16; i += 1) if(ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
     delete ctx;
 }
 
@@ -415,7 +421,7 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_d
 
 static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
                   FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr,
-                  const drt_film *scatter = nullptr, int scatter_count = 0, int scatter_rank = 0, uint64_t scatter_slice = 0)
+                  const drt_film *scatter = nullptr, int scatter_count = 0, int scatter_rank = 0, uint64_t scatter_slice = 0, bool keep_stats = false)
 {
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
@@ -447,7 +453,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
     uint64_t need = (ntasks + warps - 1) / warps;
     if(grid > need) grid = need;
-    CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
+    if(!keep_stats) CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), stream));
     cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->all_fast, ctx->nslots, (int)grid, warps, smem, stream);
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
@@ -494,12 +500,33 @@ extern "C" int drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_para
     if(rc != DRT_CUDA_OK) return rc;
     float *base = ctx->d_film;
     FilmPtrs f = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
-    rc = launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, 0);
-    if(rc != DRT_CUDA_OK) return rc;
-    CU(cudaMemcpyAsync(out->sum, f.sum, plane, cudaMemcpyDeviceToHost, 0));
-    CU(cudaMemcpyAsync(out->mean, f.mean, plane, cudaMemcpyDeviceToHost, 0));
-    CU(cudaMemcpyAsync(out->m2, f.m2, plane, cudaMemcpyDeviceToHost, 0));
-    CU(cudaMemcpyAsync(out->filter, f.filter, fplane, cudaMemcpyDeviceToHost, 0));
+    /* Large frames are rendered in row bands so that the read-back of a finished band (PCIe) runs under the render of the
+     * next one: with pinned host buffers only the last band's copy is exposed.  Rows are contiguous in every plane. */
+    const uint64_t paths = (uint64_t)npix * (params->sample_end - params->sample_begin);
+    int bands = (paths >= (1ull << 26) && params->height >= 64) ? 8 : 1;
+    if(bands > 1 && !ctx->band_render)
+    {
+        CU(cudaStreamCreateWithFlags(&ctx->band_render, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->band_copy, cudaStreamNonBlocking));
+        for(int i = 0; i < 16; i += 1) CU(cudaEventCreateWithFlags(&ctx->band_done[i], cudaEventDisableTiming));
+    }
+    cudaStream_t sr = bands > 1 ? ctx->band_render : 0, sc = bands > 1 ? ctx->band_copy : 0;
+    if(bands > 1) CU(cudaDeviceSynchronize());   /* the band streams do not synchronise with the legacy stream */
+    const size_t n = (size_t)ctx->n, w = params->width;
+    for(int b = 0; b < bands; b += 1)
+    {
+        const uint32_t y0 = (uint32_t)((uint64_t)params->height * b / bands), y1 = (uint32_t)((uint64_t)params->height * (b + 1) / bands);
+        rc = launch(ctx, params, 0, y0, params->width, y1, f, nullptr, 0, sr, nullptr, nullptr, nullptr, 0, 0, 0, b > 0);
+        if(rc != DRT_CUDA_OK) return rc;
+        if(bands > 1) { CU(cudaEventRecord(ctx->band_done[b], sr)); CU(cudaStreamWaitEvent(sc, ctx->band_done[b], 0)); }
+        const size_t at = (size_t)y0 * w * n, cnt = (size_t)(y1 - y0) * w * n * 4;
+        CU(cudaMemcpyAsync(out->sum + at, f.sum + at, cnt, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync(out->mean + at, f.mean + at, cnt, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync(out->m2 + at, f.m2 + at, cnt, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync(out->filter + (size_t)y0 * w, f.filter + (size_t)y0 * w, (size_t)(y1 - y0) * w * 4, cudaMemcpyDeviceToHost, sc));
+    }
+    ctx->last_launches = (uint64_t)bands;
+    if(bands > 1) { CU(cudaStreamSynchronize(sr)); CU(cudaStreamSynchronize(sc)); }
     CU(cudaStreamSynchronize(0));
     return DRT_CUDA_OK;
 }
