@@ -389,7 +389,7 @@ def run_b200_arm(a):
     d2h_bytes = (3 * npix * n + npix) * 4
 
     if rank == 0:
-        kinfo = ctx.render_kernel_info(a.depth)
+        kinfo = ctx.render_kernel_info(prm)
         flops_path, rc, rs, b = algorithmic_flops_per_path(scene, st, n)
         paths_launch = a.width * a.height * a.spp
         achieved_tf = flops_path * paths_launch / (kernel_ms * 1e-3) / 1e12

@@ -400,9 +400,10 @@ static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int
     return true;
 }
 
-extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_depth, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm)
+extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_render_params *params, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm)
 {
-    if(!ctx || max_depth == 0) return fail(DRT_CUDA_E_ARG, "bad argument");
+    if(!ctx || !params || params->max_depth == 0 || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "bad argument");
+    const uint32_t max_depth = params->max_depth;
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
@@ -412,8 +413,8 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_d
     size_t smem = 0;
     if(!launch_shape(ctx, L, &warps, &ctas, &smem)) return fail(DRT_CUDA_E_UNSUPPORTED, "records of max_cast_depth %u do not fit in shared memory", max_depth);
     if(name && name_len)
-        snprintf(name, name_len, "drt::render_kernel<%s,%d,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
-                 (ctx->all_fast && !ctx->f64_geometry) ? "true" : "false");
+        snprintf(name, name_len, "drt::render_kernel<%s,%d,%s,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
+                 (ctx->all_fast && !ctx->f64_geometry) ? "true" : "false", (params->sample_end - params->sample_begin >= 32) ? "true" : "false");
     if(warps_per_cta) *warps_per_cta = warps;
     if(ctas_per_sm) *ctas_per_sm = ctas;
     return DRT_CUDA_OK;

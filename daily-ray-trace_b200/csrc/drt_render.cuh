@@ -1186,6 +1186,9 @@ static __device__ __noinline__ void dump_path(float *record_dump, float *path_du
 /* ALLFAST: every surface material of the scene is a two-lobe plastic and there is exactly one light (decided by the
  * host at scene upload: all shipped Cornell boxes except the gold/glass balls of cornell_plane_light).  The kernel then
  * contains neither the general lobe evaluators nor the general shader. */
+#ifndef DRT_PARK_GENERAL
+#define DRT_PARK_GENERAL 0   /* park the film of the general kernel too (pays off only if that buys resident warps) */
+#endif
 /* PAIRED: one pixel per task with all its samples (spp >= 32) against 32/spp whole pixels per task; see the task loop. */
 template <typename R, int NS, bool ALLFAST, bool PAIRED>
 __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
@@ -1274,7 +1277,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
             /* ---- phase 1: lane = path ---- */
-            if(ALLFAST && paired) film.park(park);   /* the general kernel is bound by its 128-register code either way */
+            if((ALLFAST || DRT_PARK_GENERAL) && paired) film.park(park);
             const uint32_t q = q0 + lane;
             uint32_t bin = 9, general = 0;
             uint32_t my_px = 0, my_s = q;      /* pixel of the batch and sample index inside the pixel */
@@ -1287,7 +1290,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
                 bin = r & 255u; general = r >> 8;
             }
             __syncwarp();
-            if(ALLFAST && paired) film.unpark(park);
+            if((ALLFAST || DRT_PARK_GENERAL) && paired) film.unpark(park);
             {
                 /* termination histogram: one shared-memory atomic per distinct bin of the batch (bin 9 = idle lane) */
                 const uint32_t peers = __match_any_sync(0xffffffffu, bin);

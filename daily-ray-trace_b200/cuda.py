@@ -58,7 +58,7 @@ def lib():
         L.drt_cuda_destroy.restype = None
         L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
         L.drt_cuda_scene_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
-        L.drt_cuda_render_kernel_info.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.drt_cuda_render_kernel_info.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
         L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
@@ -127,11 +127,11 @@ class Context:
         _check(lib().drt_cuda_scene_upload_bytes(self._h, C.byref(v)))
         return v.value
 
-    def render_kernel_info(self, max_depth=4):
-        """(kernel name, warps per CTA, CTAs per SM) the uploaded scene and geometry precision select."""
+    def render_kernel_info(self, params):
+        """(kernel name, warps per CTA, CTAs per SM) the uploaded scene, the geometry precision and `params` select."""
         name = C.create_string_buffer(96)
         warps, ctas = C.c_int(), C.c_int()
-        _check(lib().drt_cuda_render_kernel_info(self._h, max_depth, name, len(name), C.byref(warps), C.byref(ctas)))
+        _check(lib().drt_cuda_render_kernel_info(self._h, C.byref(params), name, len(name), C.byref(warps), C.byref(ctas)))
         return name.value.decode(), warps.value, ctas.value
 
     def set_geometry_precision(self, precision):

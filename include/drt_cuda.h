@@ -98,9 +98,9 @@ int  drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_render_para
 int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_host);
 
 /* Which render kernel the uploaded scene and the geometry precision select, for logs and benchmark lines:
- * name = "drt::render_kernel<float,5,true>" style string (geometry type, wavelength slots per half-warp lane, all-plastic
- * specialisation), warps_per_cta and ctas_per_sm as launched for a film render with `max_depth` bounces. */
-int  drt_cuda_render_kernel_info(drt_cuda_context *ctx, uint32_t max_depth, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm);
+ * name = "drt::render_kernel<float,5,true,true>" style string (geometry type, wavelength slots per half-warp lane, all-plastic
+ * specialisation, one-pixel-per-task shape), warps_per_cta and ctas_per_sm as launched for a film render with `params`. */
+int  drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_render_params *params, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm);
 
 /* Counters of the most recent render_* / sample_paths call (waits for it to finish). */
 int  drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out);
