@@ -22,7 +22,7 @@ void        drt_launch_film_to_rgb(const void *tables, const float *plane, const
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
 void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
 void        drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream_t stream);
-void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end, uint32_t src_base,
+void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end, uint32_t src_base, uint32_t dst_base,
                                          uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream);
 size_t      drt_rgb_tables_bytes(void);
 void        drt_fill_rgb_tables(void *dst_host, const drt_tables *t);
@@ -59,6 +59,7 @@ struct drt_cuda_context
     /* library-owned film + dump buffers for the host-buffer entry points */
     float *d_film = nullptr; size_t film_bytes = 0;
     float *d_dump = nullptr; size_t dump_bytes = 0;
+    float *d_slice = nullptr; size_t slice_bytes = 0;   /* merged planes of this rank's slice before they are copied to the root */
     uint64_t launches = 0;
     size_t upload_bytes = 0;
     uint64_t last_launches = 0;
@@ -100,7 +101,7 @@ extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
-    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats); cudaFree(ctx->d_counter); cudaFree(ctx->d_film); cudaFree(ctx->d_dump);
+    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats); cudaFree(ctx->d_counter); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice);
     if(ctx->band_render) cudaStreamDestroy(ctx->band_render);
     if(ctx->band_copy) cudaStreamDestroy(ctx->band_copy);
     for(int i = 0; i < 16; i += 1) if(ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
@@ -733,7 +734,7 @@ extern "C" int drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *d
     FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 };
     if(pixel_end > pixel_begin)
     {
-        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, 0u, bgra_sum, bgra_mean, bgra_var,
+        drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, 0u, 0u, bgra_sum, bgra_mean, bgra_var,
                                      ctx->num_sms * 8, (cudaStream_t)stream);
         CU(cudaGetLastError());
         ctx->launches += 1;
@@ -756,12 +757,24 @@ extern "C" int drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film 
     for(int g = 0; g < count; g += 1)   /* rank g's partial film of this slice: staging pixels [g * slice, (g + 1) * slice) */
         films[g] = FilmPtrs{ staging->sum + (size_t)g * slice_pixels * n, staging->filter + (size_t)g * slice_pixels,
                              staging->mean + (size_t)g * slice_pixels * n, staging->m2 + (size_t)g * slice_pixels * n };
-    FilmPtrs d = { dst->sum, dst->filter, dst->mean, dst->m2 };
     if(pixel_end > pixel_begin)
     {
+        /* merged planes of the slice go to a local scratch film first and travel to dst_device (the root's film: usually peer
+         * memory) as four contiguous copies: the copy engines move large blocks over NVLink about twice as fast as the
+         * kernel's 4-byte-per-lane peer stores did (measured: 763 MB into the root in 2.2 ms from kernel stores) */
+        const size_t spx = (size_t)(pixel_end - pixel_begin), plane = spx * n * 4;
+        int rc = ensure(&ctx->d_slice, &ctx->slice_bytes, 3 * plane + spx * 4);
+        if(rc != DRT_CUDA_OK) return rc;
+        float *base = ctx->d_slice;
+        FilmPtrs d = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
         drt_launch_film_gather_merge(ctx->d_rgb_tables, count, films, d, (uint32_t)pixel_begin, (uint32_t)pixel_end, (uint32_t)pixel_begin,
-                                     bgra_sum, bgra_mean, bgra_var, ctx->num_sms * 8, (cudaStream_t)stream);
+                                     (uint32_t)pixel_begin, bgra_sum, bgra_mean, bgra_var, ctx->num_sms * 8, (cudaStream_t)stream);
         CU(cudaGetLastError());
+        const size_t at = (size_t)pixel_begin * n;
+        CU(cudaMemcpyAsync(dst->sum + at, d.sum, plane, cudaMemcpyDefault, (cudaStream_t)stream));
+        CU(cudaMemcpyAsync(dst->mean + at, d.mean, plane, cudaMemcpyDefault, (cudaStream_t)stream));
+        CU(cudaMemcpyAsync(dst->m2 + at, d.m2, plane, cudaMemcpyDefault, (cudaStream_t)stream));
+        CU(cudaMemcpyAsync(dst->filter + pixel_begin, d.filter, spx * 4, cudaMemcpyDefault, (cudaStream_t)stream));
         ctx->launches += 1;
     }
     return DRT_CUDA_OK;

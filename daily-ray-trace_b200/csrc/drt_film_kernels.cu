@@ -131,7 +131,7 @@ struct FilmSet { int count; FilmPtrs film[16]; };
 
 template <int CHUNK>
 __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables *tables, FilmSet set, FilmPtrs dst, uint32_t pixel_begin,
-                                                                uint32_t pixel_end, uint32_t src_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
+                                                                uint32_t pixel_end, uint32_t src_base, uint32_t dst_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var)
 {
     __shared__ RgbTables t;
     for(uint32_t i = threadIdx.x; i < sizeof(RgbTables) / 4; i += blockDim.x)
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(256) film_gather_merge_kernel(const RgbTables 
         {
             uint32_t wl = lane + k * 32;
             if(wl >= n) continue;
-            size_t at = (size_t)p * n + wl;
+            size_t at = (size_t)(p - dst_base) * n + wl;   /* the destination is indexed from dst_base (0: a whole film) */
             dst.sum[at] = sum[k]; dst.mean[at] = mean[k]; dst.m2[at] = m2[k];
             if(m2[k] > peak) peak = m2[k];
         }
-        if(lane == 0) dst.filter[p] = cnt;
+        if(lane == 0) dst.filter[p - dst_base] = cnt;
         if(!bgra_sum) continue;
         peak = warp_max(peak);
         float acc[9];
@@ -289,16 +289,16 @@ void drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream
 }
 
 void drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end,
-                                  uint32_t src_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream)
+                                  uint32_t src_base, uint32_t dst_base, uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream)
 {
     drt::FilmSet set;
     set.count = count;
     for(int i = 0; i < count && i < 16; i += 1) set.film[i] = films[i];
     if(count <= 2)
-        drt::film_gather_merge_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base,
+        drt::film_gather_merge_kernel<2><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base, dst_base,
                                                                   bgra_sum, bgra_mean, bgra_var);
     else
-        drt::film_gather_merge_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base,
+        drt::film_gather_merge_kernel<4><<<grid, 256, 0, stream>>>(reinterpret_cast<const drt::RgbTables *>(tables), set, dst, pixel_begin, pixel_end, src_base, dst_base,
                                                                   bgra_sum, bgra_mean, bgra_var);
 }
 
