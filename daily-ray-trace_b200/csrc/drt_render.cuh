@@ -45,7 +45,7 @@ template <typename R> __device__ __forceinline__ V3<R> cross(V3<R> a, V3<R> b)
 
 /* MUFU.RCP alone (<= 1 ulp), for arguments known to be in range */
 __device__ __forceinline__ float r_rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float  r_sqrt(float x)  { return sqrtf(x); }
+__device__ __forceinline__ float  r_sqrt(float x)  { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   /* MUFU.SQRT alone */
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ float  r_abs(float x)   { return fabsf(x); }
 __device__ __forceinline__ double r_abs(double x)  { return fabs(x); }
@@ -103,7 +103,7 @@ template <typename R> __device__ __forceinline__ V3<R> reflect(V3<R> v, V3<R> n)
 template <typename R> __device__ __forceinline__ V3<R> transmit(V3<R> v, V3<R> n, R ir, R tr)   /* geometry.c:92-106 */
 {
     R vn = dot(v, n);
-    R rel = ir / tr;
+    R rel = r_div(ir, tr);
     V3<R> m = n * vn;
     v = m - v;
     V3<R> perpend = neg(v * rel);
@@ -401,17 +401,17 @@ static __device__ __noinline__ void eval_weights_general(const GeomT<R> &g, int 
                 R d = dot(nrm, mn), gg = R(0);
                 if(d > R(0))
                 {
-                    R d2 = d * d, d4 = d2 * d2, tan_sq = (R(1) / d2) - R(1);
-                    gg = r2 / (Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
+                    R d2 = d * d, d4 = d2 * d2, tan_sq = r_div(R(1), d2) - R(1);
+                    gg = r_div(r2, Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
                 }
                 R v_mn = dot(out, mn), v_sn = dot(out, nrm);
-                R quot = r_abs(v_mn / v_sn), att = R(0);
+                R quot = r_abs(r_div(v_mn, v_sn)), att = R(0);
                 if(!(quot <= R(0)))
                 {
-                    R tan_sq = (R(1) / (v_sn * v_sn)) - R(1);
-                    att = R(2) / (R(1) + r_sqrt(R(1) + r2 * tan_sq));
+                    R tan_sq = r_div(R(1), v_sn * v_sn) - R(1);
+                    att = r_div(R(2), R(1) + r_sqrt(R(1) + r2 * tan_sq));
                 }
-                kind = BK_COND_MN; val = (float)((gg * att) * (R(1) / (R(4) * on_dot)));
+                kind = BK_COND_MN; val = (float)((gg * att) * r_div(R(1), R(4) * on_dot));
                 mn_cos = (float)mn_dot;
                 break;
             }
@@ -531,7 +531,7 @@ static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT
             }
             q.z = r_sqrt(R(1) - dot(q, q));
             in = rotate_from_z<R>(h.nrm, q);
-            inv_pdf = Num<R>::pi() / dot(h.nrm, in);
+            inv_pdf = r_div(Num<R>::pi(), dot(h.nrm, in));
             break;
         }
         case DRT_DIR_SPECULAR:   /* :215-220 */
@@ -548,18 +548,18 @@ static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT
         {
             R ra = fresnel_dielectric<R>(g.refr_a[h.inc_mat], g.refr_a[h.trans_mat], h.on_dot);
             R rb = fresnel_dielectric<R>(g.refr_b[h.inc_mat], g.refr_b[h.trans_mat], h.on_dot);
-            R rd = ra + (g.trans_num * ((rb - ra) / g.trans_den));
+            R rd = ra + (g.trans_num * r_div(rb - ra, g.trans_den));
             R f = rng.unit<R>();
             if(f < rd)
             {
                 in = reflect<R>(neg(h.out), h.nrm);
-                inv_pdf = R(1) / rd;
+                inv_pdf = r_div(R(1), rd);
                 match = 1;
             }
             else
             {
                 in = transmit<R>(neg(h.out), h.nrm, g.n630[h.inc_mat], g.n630[h.trans_mat]);
-                inv_pdf = R(1) / (R(1) - rd);
+                inv_pdf = r_div(R(1), R(1) - rd);
                 match = ((in.x == in.x) && (in.y == in.y) && (in.z == in.z)) ? 2 : 0;
             }
             break;
@@ -571,8 +571,8 @@ static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT
             {
                 R f = rng.unit<R>();
                 R gq = rng.unit<R>();
-                R tan_mn = (rough * r_sqrt(f)) / r_sqrt(R(1) - f);
-                R cos_mn = R(1) / r_sqrt(R(1) + tan_mn * tan_mn);
+                R tan_mn = r_div(rough * r_sqrt(f), r_sqrt(R(1) - f));
+                R cos_mn = r_rsqrt(R(1) + tan_mn * tan_mn);
                 R cm2 = cos_mn * cos_mn;
                 R sin_mn = r_sqrt((cm2 < R(1)) ? R(1) - cm2 : R(0));   /* 1/sqrt(1+t^2) may round to 1+ulp with approximate division */
                 R s, c;
@@ -585,11 +585,11 @@ static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT
                 R d = R(0);   /* ggx(n, mn, rough) * sn_mn */
                 if(sn_mn > R(0))
                 {
-                    R r2 = rough * rough, d2 = sn_mn * sn_mn, d4 = d2 * d2, tan_sq = (R(1) / d2) - R(1);
-                    d = r2 / (Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
+                    R r2 = rough * rough, d2 = sn_mn * sn_mn, d4 = d2 * d2, tan_sq = r_div(R(1), d2) - R(1);
+                    d = r_div(r2, Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
                 }
                 d = d * sn_mn;
-                inv_pdf = (R(4) * o_mn) / d;
+                inv_pdf = r_div(R(4) * o_mn, d);
             }
             while(dot(in, h.nrm) < R(0));
             break;
@@ -659,7 +659,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
     if(g.ap_radius > R(0))
     {
         V3<R> focus_dir = normalise(ap - point);
-        focus_dir = focus_dir * (g.focal_depth / dot(focus_dir, fwd));
+        focus_dir = focus_dir * r_div(g.focal_depth, dot(focus_dir, fwd));
         V3<R> focus_point = point + focus_dir;
         V3<R> disc = sample_disc<R>(rng) * g.ap_radius;
         V3<R> lens = mk<R>(g.lens_rot[0] * disc.x + g.lens_rot[3] * disc.y + g.lens_rot[6] * disc.z,
