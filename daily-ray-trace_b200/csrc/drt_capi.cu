@@ -164,21 +164,53 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         if(f->normal[a] != 1.0 && f->normal[a] != -1.0) return -1;
         return a;
     };
+    /* boundary plane: every other surface (rectangle corners, sphere extents, points) lies in one closed half-space of it */
+    auto is_boundary = [&](int i) -> bool {
+        const drt_surface *f = &s->surfaces[i];
+        if(f->type != DRT_GEO_PLANE) return false;
+        const double eps = 1e-6;   /* two orders below the reference's 1e-4 ray offset */
+        double lo = 0.0, hi = 0.0;
+        auto side = [&](const double *q, double r) {
+            double d = (q[0] - f->position[0]) * f->normal[0] + (q[1] - f->position[1]) * f->normal[1] + (q[2] - f->position[2]) * f->normal[2];
+            if(d - r < lo) lo = d - r;
+            if(d + r > hi) hi = d + r;
+        };
+        for(int j = 0; j < s->num_surfaces; j += 1)
+        {
+            if(j == i) continue;
+            const drt_surface *o = &s->surfaces[j];
+            if(o->type == DRT_GEO_PLANE)
+                for(int c = 0; c < 4; c += 1)
+                {
+                    double q[3];
+                    for(int k = 0; k < 3; k += 1) q[k] = o->position[k] + ((c & 1) ? o->u[k] : 0.0) + ((c & 2) ? o->v[k] : 0.0);
+                    side(q, 0.0);
+                }
+            else side(o->position, o->type == DRT_GEO_SPHERE ? o->radius : 0.0);
+        }
+        return lo >= -eps || hi <= eps;
+    };
     int slot = 0;
-    for(int pass = 0; pass < 5; pass += 1)
+    for(int pass = 0; pass < 9; pass += 1)   /* passes 0-7: plane group (pass / 2), boundary planes first; pass 8: spheres */
         for(int i = 0; i < s->num_surfaces; i += 1)
         {
             const drt_surface *f = &s->surfaces[i];
-            if(pass < 4) { if(f->type != DRT_GEO_PLANE || plane_axis(f) != (pass < 3 ? pass : -1)) continue; }
+            const int group = pass / 2;
+            if(pass < 8)
+            {
+                if(f->type != DRT_GEO_PLANE || plane_axis(f) != (group < 3 ? group : -1)) continue;
+                if(is_boundary(i) != ((pass & 1) == 0)) continue;
+                if((pass & 1) == 0) g->nax_b[group] += 1;
+            }
             else if(f->type != DRT_GEO_SPHERE) continue;
             g->sid[slot] = i;
             g->N4[slot] = R4<R>{ g->nx[i], g->ny[i], g->nz[i], (R)0 };
             g->P4[slot] = R4<R>{ g->px[i], g->py[i], g->pz[i], g->rad[i] };
             g->U4[slot] = R4<R>{ g->unx[i], g->uny[i], g->unz[i], g->ulen[i] };
             g->V4[slot] = R4<R>{ g->vnx[i], g->vny[i], g->vnz[i], g->vlen[i] };
-            if(pass < 3)
+            if(group < 3)
             {
-                const int a = pass, b = (a == 0) ? 1 : 0, c = (a == 2) ? 1 : 2;   /* in-plane axes b < c */
+                const int a = group, b = (a == 0) ? 1 : 0, c = (a == 2) ? 1 : 2;   /* in-plane axes b < c */
                 double lo[2], hi[2];
                 const int bc[2] = { b, c };
                 for(int k = 0; k < 2; k += 1)
@@ -191,7 +223,7 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
                 g->nax[a] += 1;
             }
             slot += 1;
-            if(pass < 4) g->nplanes += 1; else g->nspheres += 1;
+            if(pass < 8) g->nplanes += 1; else g->nspheres += 1;
         }
     for(int m = 0; m < s->num_materials; m += 1)
     {

@@ -46,6 +46,11 @@ struct GeomT
      * AX4[slot] = { p_a, centre_b, half extent_b, centre_c }, AXH[slot] = { half extent_c, scene index as a number }. */
     int   nplanes, nspheres, pad2, pad3;
     int   nax[4];                  /* [3] unused */
+    /* Inside each plane group the BOUNDARY planes come first: planes with the whole scene in one of their closed half-spaces (every
+     * wall of a room).  A segment between two points of the scene can meet such a plane only at its end points, where the
+     * reference's shadow test never reports a hit (origin pushed 1e-4 along the ray, Q2; far end excluded by vis_dist,
+     * daily_ray_trace.c:244-250), so shadow rays skip them: nax_b[0..2] of the axis groups, nax_b[3] of the general planes. */
+    int   nax_b[4];
     R4<R> AX4[DRT_MAX_SURFACES];
     R2<R> AXH[DRT_MAX_SURFACES];
     int   sid[DRT_MAX_SURFACES];

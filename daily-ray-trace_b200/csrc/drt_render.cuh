@@ -262,7 +262,7 @@ __device__ __forceinline__ void nearest_axis_group(const GeomT<R> &g, int k0, in
     }
 }
 
-template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, int skip, R *dist_out)
+template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R> &g, V3<R> o, V3<R> d, R limit, int skip, bool shadow, R *dist_out)
 {
     R best = limit, best_sid = R(-1);
     int found = -1;
@@ -271,11 +271,13 @@ template <typename R> __device__ __noinline__ int nearest_surface(const GeomT<R>
      * the current best (coplanar surfaces, a ray through a shared edge) replaces it only if its scene index is lower. */
     const int nx = g.nax[0], ny = nx + g.nax[1], nz = ny + g.nax[2];
     const int np = g.nplanes, ns = g.nspheres;
-    nearest_axis_group<R>(g, 0, nx, o.x, o.y, o.z, r_rcp(d.x), d.y, d.z, skip, best, best_sid, found);
-    nearest_axis_group<R>(g, nx, ny, o.y, o.x, o.z, r_rcp(d.y), d.x, d.z, skip, best, best_sid, found);
-    nearest_axis_group<R>(g, ny, nz, o.z, o.x, o.y, r_rcp(d.z), d.x, d.y, skip, best, best_sid, found);
+    /* shadow rays start every plane group after its boundary planes (GeomT::nax_b) */
+    const int bx = shadow ? g.nax_b[0] : 0, by = shadow ? g.nax_b[1] : 0, bz = shadow ? g.nax_b[2] : 0, bg = shadow ? g.nax_b[3] : 0;
+    nearest_axis_group<R>(g, bx, nx, o.x, o.y, o.z, r_rcp(d.x), d.y, d.z, skip, best, best_sid, found);
+    nearest_axis_group<R>(g, nx + by, ny, o.y, o.x, o.z, r_rcp(d.y), d.x, d.z, skip, best, best_sid, found);
+    nearest_axis_group<R>(g, ny + bz, nz, o.z, o.x, o.y, r_rcp(d.z), d.x, d.y, skip, best, best_sid, found);
 #pragma unroll 1
-    for(int k = nz; k < np; k += 1)
+    for(int k = nz + bg; k < np; k += 1)
     {
         if(k == skip) continue;
         R dist;
@@ -309,7 +311,7 @@ template <typename R> __device__ __forceinline__ bool closest_hit(const GeomT<R>
 {
     o = o + d * Num<R>::fudge();   /* Q2 */
     R best;
-    int slot = nearest_surface<R>(g, o, d, Num<R>::inf(), skip, &best);
+    int slot = nearest_surface<R>(g, o, d, Num<R>::inf(), skip, false, &best);
     if(slot < 0) return false;
     const int found = g.sid[slot];
     h.plane_slot = (slot < g.nplanes) ? slot : -1;
@@ -339,7 +341,9 @@ template <typename R> __device__ __forceinline__ bool visible(const GeomT<R> &g,
     V3<R> po = p1 - o;
     R vis_dist = r_sqrt(dot(po, po)) - Num<R>::fudge();
     R t;
-    return nearest_surface<R>(g, o, dir, vis_dist, skip, &t) < 0;
+    /* nothing but boundary planes in the scene (an empty room): no surface can lie between two of its points */
+    if(g.nax_b[0] + g.nax_b[1] + g.nax_b[2] + g.nax_b[3] == g.nplanes && g.nspheres == 0) return true;
+    return nearest_surface<R>(g, o, dir, vis_dist, skip, true, &t) < 0;
 }
 
 /* ------------------------------------------------------------------ BSDF evaluation reduced to basis weights
