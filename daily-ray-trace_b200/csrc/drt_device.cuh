@@ -20,7 +20,7 @@
 #define DRT_CTA_WARPS 8      /* warps per CTA of the general kernel */
 #endif
 #ifndef DRT_FAST_WARPS
-#define DRT_FAST_WARPS 16     /* warps per CTA of the ALLFAST kernel: 2 CTAs x 16 warps x 64 registers fill an SM (measured: 8 -> 16 warps = +21 % paths/s) */
+#define DRT_FAST_WARPS 14     /* warps per CTA of the ALLFAST kernel: 2 CTAs x 14 warps x 72 registers per SM (measured: 8 warps 6.7, 12: 9.70, 14: 9.79, 16: 9.65 G paths/s) */
 #endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS
