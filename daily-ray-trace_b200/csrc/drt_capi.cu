@@ -48,6 +48,8 @@ struct drt_cuda_context
     bool   have_scene = false;
     bool   f64_geometry = false;
     int    n = 0, nslots = 0, nlights = 0, eval_words = 1;
+    bool   hit_bound = false;      /* hit_u/v: film-plane bound (in pixel units of the uploaded camera) of everything a camera ray can hit */
+    double hit_u0 = 0, hit_u1 = 0, hit_v0 = 0, hit_v1 = 0;
     bool   all_fast = false;      /* every surface material has a plastic block (SpdIndex::plastic): the specialised kernel applies */
     void  *d_geom32 = nullptr, *d_geom64 = nullptr;
     SpdIndex *d_index = nullptr;
@@ -285,6 +287,54 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     fill_geom(g32, scene, camera);
     fill_geom(g64, scene, camera);
 
+    /* Screen-space bound of the scene for a pinhole camera: the film point whose ray passes through a world point Q is
+     * P = ap + (ap - Q) * f / depth(Q) (sample_scene :602-607: the ray starts on the film and runs through the aperture), so the
+     * projection of a convex surface is the hull of its projected corners as long as every corner is in front of the aperture. */
+    ctx->hit_bound = false;
+    if(camera->aperture_radius == 0.0)
+    {
+        const double *ap = camera->aperture_position, *fw = camera->forward;
+        double fd = 0.0;
+        for(int k = 0; k < 3; k += 1) fd += (ap[k] - camera->film_bottom_left[k]) * fw[k];
+        double g_rr = 0.0, g_uu = 0.0, g_ru = 0.0;
+        for(int k = 0; k < 3; k += 1) { g_rr += camera->right[k] * camera->right[k]; g_uu += camera->up[k] * camera->up[k]; g_ru += camera->right[k] * camera->up[k]; }
+        const double g_det = g_rr * g_uu - g_ru * g_ru;
+        bool ok = fd > 0.0 && camera->pixel_width > 0.0 && camera->pixel_height > 0.0 && g_det > 1e-12;
+        double u0 = 1e300, u1 = -1e300, v0 = 1e300, v1 = -1e300;
+        auto project = [&](const double *q) {
+            double depth = 0.0;
+            for(int k = 0; k < 3; k += 1) depth += (q[k] - ap[k]) * fw[k];
+            if(!(depth > 1e-9)) { ok = false; return; }
+            double dr = 0.0, du = 0.0;   /* (P - film_bottom_left) = a * right + b * up: solve for a, b (no orthonormality assumed) */
+            for(int k = 0; k < 3; k += 1)
+            {
+                double pk = ap[k] + (ap[k] - q[k]) * (fd / depth) - camera->film_bottom_left[k];
+                dr += pk * camera->right[k]; du += pk * camera->up[k];
+            }
+            double u = (dr * g_uu - du * g_ru) / g_det / camera->pixel_width, v = (du * g_rr - dr * g_ru) / g_det / camera->pixel_height;
+            if(u < u0) u0 = u; if(u > u1) u1 = u; if(v < v0) v0 = v; if(v > v1) v1 = v;
+        };
+        for(int i = 0; i < scene->num_surfaces && ok; i += 1)
+        {
+            const drt_surface *f = &scene->surfaces[i];
+            if(f->type == DRT_GEO_PLANE)
+                for(int c = 0; c < 4; c += 1)
+                {
+                    double q[3];
+                    for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + ((c & 1) ? f->u[k] : 0.0) + ((c & 2) ? f->v[k] : 0.0);
+                    project(q);
+                }
+            else if(f->type == DRT_GEO_SPHERE)
+                for(int c = 0; c < 8; c += 1)   /* corners of the sphere's bounding cube */
+                {
+                    double q[3];
+                    for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + (((c >> k) & 1) ? f->radius : -f->radius);
+                    project(q);
+                }
+        }
+        if(ok && u0 <= u1) { ctx->hit_bound = true; ctx->hit_u0 = u0; ctx->hit_u1 = u1; ctx->hit_v0 = v0; ctx->hit_v1 = v1; }
+    }
+
     /* spectrum pool: row 0 = zeros, then one row per SPD a material was given */
     SpdIndex index;
     memset(&index, 0, sizeof(index));
@@ -474,6 +524,13 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
     for(int i = 0; i < scatter_count; i += 1) L.scatter[i] = FilmPtrs{ scatter[i].sum, scatter[i].filter, scatter[i].mean, scatter[i].m2 };
     L.scatter_count = (uint32_t)scatter_count; L.scatter_rank = (uint32_t)scatter_rank; L.scatter_slice = (uint32_t)scatter_slice;
+    L.hit_x0 = 0; L.hit_y0 = 0; L.hit_x1 = p->width; L.hit_y1 = p->height;
+    if(ctx->hit_bound)   /* one pixel of slack on every side: the f32 camera arithmetic of the kernel against this f64 projection */
+    {
+        auto clampi = [](double v, uint32_t hi) -> uint32_t { return v <= 0.0 ? 0u : v >= (double)hi ? hi : (uint32_t)v; };
+        L.hit_x0 = clampi(floor(ctx->hit_u0) - 1.0, p->width);  L.hit_x1 = clampi(ceil(ctx->hit_u1) + 1.0, p->width);
+        L.hit_y0 = clampi(floor(ctx->hit_v0) - 1.0, p->height); L.hit_y1 = clampi(ceil(ctx->hit_v1) + 1.0, p->height);
+    }
     record_layout(ctx, p->max_depth, L);
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     int warps, ctas_per_sm;

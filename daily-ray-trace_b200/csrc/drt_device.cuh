@@ -153,6 +153,10 @@ struct RenderLaunch
      * rank's partial film of it is written -- over NVLink when the owner is a peer -- into the owner's staging film at pixel
      * scatter_rank * scatter_slice + p % scatter_slice, so every owner ends up with all ranks' partial films of its slice in
      * local memory.  scatter_count = 0: plain store to `film`. */
+    /* Pixels outside [hit_x0, hit_x1) x [hit_y0, hit_y1) cannot see any surface (pinhole camera: a conservative screen-space
+     * bound of the scene's projection, computed at upload); their camera paths all end on the escape material at depth 0
+     * (cast_ray :451-452), so they are counted, not traced.  The full image when no bound is known. */
+    uint32_t hit_x0, hit_y0, hit_x1, hit_y1;
     uint32_t scatter_count, scatter_rank, scatter_slice;
     uint32_t task_rotate;          /* tasks are walked from this index (mod the task count): with scatter_rank * slice every rank starts in its own
                                     * slice, so at any moment each owner receives from one peer instead of from all of them */

@@ -1278,6 +1278,20 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
         const uint32_t task_x = L.x0 + p_begin % rw, task_y = L.y0 + p_begin / rw;   /* first pixel of the task */
         if(paired && L.accumulate && have_film) film = film_load<NS>(L.film, task_y * L.width + task_x, n, lane);
 
+        if(paired && !dumping && (task_x < L.hit_x0 || task_x >= L.hit_x1 || task_y < L.hit_y0 || task_y >= L.hit_y1))
+        {
+            /* a pixel that cannot see a surface: all its samples at once */
+            if(half == 0) film.add_zeros(total);
+            if(lane == 0)
+            {
+                atomicAdd(&s_stats[1], (unsigned long long)total);
+                atomicAdd(&s_stats[4], (unsigned long long)((L.pixel_scheme == DRT_PIXEL_RANDOM) ? 2u * total : 0u));
+                atomicAdd(&s_stats[5], (unsigned long long)total);
+            }
+            film.merge_halves();
+            if(have_film) store_pixel(task_y * L.width + task_x, film);
+            continue;
+        }
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
             /* ---- phase 1: lane = path ---- */
@@ -1290,8 +1304,19 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
             {
                 uint32_t x = task_x, y = task_y;
                 if(!paired) { const uint32_t lp = p_begin + my_px; x = L.x0 + lp % rw; y = L.y0 + lp / rw; }
-                uint32_t r = trace_path<R, ALLFAST>(g, ix, L, rec + lane * stride, x, y, L.sample_begin + my_s, tally);
-                bin = r & 255u; general = r >> 8;
+                if(x < L.hit_x0 || x >= L.hit_x1 || y < L.hit_y0 || y >= L.hit_y1)
+                {
+                    /* the pixel cannot see a surface (RenderLaunch::hit_*): its path is the camera ray's two draws and one closest-hit
+                     * ray that ends on the escape material */
+                    rec[lane * stride + REC_NB] = 0.f;
+                    tally[0] += 1; tally[3] += (L.pixel_scheme == DRT_PIXEL_RANDOM) ? 2u : 0u;
+                    bin = 0;
+                }
+                else
+                {
+                    uint32_t r = trace_path<R, ALLFAST>(g, ix, L, rec + lane * stride, x, y, L.sample_begin + my_s, tally);
+                    bin = r & 255u; general = r >> 8;
+                }
             }
             __syncwarp();
             if((ALLFAST || DRT_PARK_GENERAL) && paired) film.unpark(park);

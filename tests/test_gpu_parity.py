@@ -94,6 +94,34 @@ def test_film_matches_oracle(ctx):
     assert scale > 0
 
 
+@pytest.mark.parametrize("scene,w,h,spp", [("init_cornell", 64, 48, 33), ("init_cornell", 40, 56, 5), ("cornell_downward", 48, 48, 32),
+                                           ("first_scene", 40, 30, 34)])
+def test_full_frame_with_unseen_pixels(ctx, scene, w, h, spp):
+    """Whole frames of scenes that fill only part of the image: pixels outside the screen-space bound of the scene are counted, not
+    traced (RenderLaunch::hit_*), in both task shapes.  The film and every work counter must equal the oracle's, which traces them."""
+    depth = 4
+    cfg, tables, sc, camera = common.load(scene, w, h, spp, depth)
+    ctx.upload_scene(sc, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 5)
+    film = ctx.render_host(prm)
+    st = ctx.stats()
+    o_sum, o_avg, o_m2, _, cnt = oracledriver.render_tile(sc, camera, prm, 0, 0, w, h)
+    n = sc.num_wavelengths
+    assert np.array_equal(film["filter"], o_sum[:, n].astype(np.float32))
+    lit_ref, lit_gpu = np.abs(o_sum[:, :n]).max(axis=1) > 0, np.abs(film["sum"]).max(axis=1) > 0
+    print(f"\n{scene} {w}x{h}x{spp}: {100 * (1 - lit_ref.mean()):.1f} % of the pixels see nothing")
+    assert np.array_equal(lit_ref, lit_gpu)                      # no pixel that receives light was skipped, none was invented
+    bad = np.zeros(w * h, bool)
+    for name, ref in (("sum", o_sum[:, :n]), ("mean", o_avg), ("m2", o_m2)):
+        floor = 1e-5 * np.abs(ref).max()
+        bad |= (np.abs(film[name] - ref) / np.maximum(np.abs(ref), floor)).max(axis=1) > 2e-3
+    assert bad.mean() <= 0.003
+    assert st.paths == cnt.paths == w * h * spp
+    assert abs(int(st.closest_rays) - int(cnt.closest_rays)) <= 4 * max(int(bad.sum()), 1) * spp
+    assert int(st.rng_draws) >= 2 * w * h * spp
+
+
 def test_sample_ranges_compose(ctx):
     """Rendering [0,a) then accumulating [a,b) equals rendering [0,b): same per-path streams; the partial films are merged in a
     different order (pairwise update of count/mean/M2), so planes agree to rounding, the sample count exactly."""
