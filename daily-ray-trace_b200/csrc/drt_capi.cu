@@ -118,6 +118,108 @@ static double value_at_wl(const drt_scene *s, const double *spd, double wl)
     return spd[i0] + ((wl - w0) * ((spd[i1] - spd[i0]) / (w1 - w0)));
 }
 
+/* Screen-space bound of the scene for a pinhole camera: the film point whose ray passes through a world point Q is
+ * P = ap + (ap - Q) * f / depth(Q) (sample_scene :602-607: the ray starts on the film and runs through the aperture), so the
+ * projection of a convex surface is the hull of its projected corners as long as every corner is in front of the aperture.
+ * Returns false (no bound) for a thin lens or when a surface reaches behind the aperture.  Pure host arithmetic. */
+static bool scene_hit_bound(const drt_scene *scene, const drt_camera *camera, double *out_u0, double *out_u1, double *out_v0, double *out_v1)
+{
+    if(camera->aperture_radius != 0.0) return false;
+    const double *ap = camera->aperture_position, *fw = camera->forward;
+    double fd = 0.0;
+    for(int k = 0; k < 3; k += 1) fd += (ap[k] - camera->film_bottom_left[k]) * fw[k];
+    double g_rr = 0.0, g_uu = 0.0, g_ru = 0.0;
+    for(int k = 0; k < 3; k += 1) { g_rr += camera->right[k] * camera->right[k]; g_uu += camera->up[k] * camera->up[k]; g_ru += camera->right[k] * camera->up[k]; }
+    const double g_det = g_rr * g_uu - g_ru * g_ru;
+    bool ok = fd > 0.0 && camera->pixel_width > 0.0 && camera->pixel_height > 0.0 && g_det > 1e-12;
+    double u0 = 1e300, u1 = -1e300, v0 = 1e300, v1 = -1e300;
+    auto project = [&](const double *q) {
+        double depth = 0.0;
+        for(int k = 0; k < 3; k += 1) depth += (q[k] - ap[k]) * fw[k];
+        if(!(depth > 1e-9)) { ok = false; return; }
+        double dr = 0.0, du = 0.0;   /* (P - film_bottom_left) = a * right + b * up: solve for a, b (no orthonormality assumed) */
+        for(int k = 0; k < 3; k += 1)
+        {
+            double pk = ap[k] + (ap[k] - q[k]) * (fd / depth) - camera->film_bottom_left[k];
+            dr += pk * camera->right[k]; du += pk * camera->up[k];
+        }
+        double u = (dr * g_uu - du * g_ru) / g_det / camera->pixel_width, v = (du * g_rr - dr * g_ru) / g_det / camera->pixel_height;
+        if(u < u0) u0 = u; if(u > u1) u1 = u; if(v < v0) v0 = v; if(v > v1) v1 = v;
+    };
+    for(int i = 0; i < scene->num_surfaces && ok; i += 1)
+    {
+        const drt_surface *f = &scene->surfaces[i];
+        if(f->type == DRT_GEO_PLANE)
+            for(int c = 0; c < 4; c += 1)
+            {
+                double q[3];
+                for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + ((c & 1) ? f->u[k] : 0.0) + ((c & 2) ? f->v[k] : 0.0);
+                project(q);
+            }
+        else if(f->type == DRT_GEO_SPHERE)
+            for(int c = 0; c < 8; c += 1)   /* corners of the sphere's bounding cube */
+            {
+                double q[3];
+                for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + (((c >> k) & 1) ? f->radius : -f->radius);
+                project(q);
+            }
+    }
+    if(!(ok && u0 <= u1)) return false;
+    *out_u0 = u0; *out_u1 = u1; *out_v0 = v0; *out_v1 = v1;
+    return true;
+}
+
+/* the pixel rectangle of a bound, with one pixel of slack on every side (f32 camera arithmetic of the kernel against the f64 projection) */
+static void hit_rect(bool have, double u0, double u1, double v0, double v1, uint32_t width, uint32_t height, uint32_t rect[4])
+{
+    rect[0] = 0; rect[1] = 0; rect[2] = width; rect[3] = height;
+    if(!have) return;
+    auto clampi = [](double v, uint32_t hi) -> uint32_t { return v <= 0.0 ? 0u : v >= (double)hi ? hi : (uint32_t)v; };
+    rect[0] = clampi(floor(u0) - 1.0, width);  rect[2] = clampi(ceil(u1) + 1.0, width);
+    rect[1] = clampi(floor(v0) - 1.0, height); rect[3] = clampi(ceil(v1) + 1.0, height);
+}
+
+/* boundary plane: every other surface (rectangle corners, sphere extents, points) lies in one closed half-space of it, so a segment
+ * between two points of the scene can meet it only at its end points (GeomT::nax_b) */
+static bool surface_is_boundary(const drt_scene *s, int i)
+{
+    const drt_surface *f = &s->surfaces[i];
+    if(f->type != DRT_GEO_PLANE) return false;
+    const double eps = 1e-6;   /* two orders below the reference's 1e-4 ray offset */
+    double lo = 0.0, hi = 0.0;
+    auto side = [&](const double *q, double r) {
+        double d = (q[0] - f->position[0]) * f->normal[0] + (q[1] - f->position[1]) * f->normal[1] + (q[2] - f->position[2]) * f->normal[2];
+        if(d - r < lo) lo = d - r;
+        if(d + r > hi) hi = d + r;
+    };
+    for(int j = 0; j < s->num_surfaces; j += 1)
+    {
+        if(j == i) continue;
+        const drt_surface *o = &s->surfaces[j];
+        if(o->type == DRT_GEO_PLANE)
+            for(int c = 0; c < 4; c += 1)
+            {
+                double q[3];
+                for(int k = 0; k < 3; k += 1) q[k] = o->position[k] + ((c & 1) ? o->u[k] : 0.0) + ((c & 2) ? o->v[k] : 0.0);
+                side(q, 0.0);
+            }
+        else side(o->position, o->type == DRT_GEO_SPHERE ? o->radius : 0.0);
+    }
+    return lo >= -eps || hi <= eps;
+}
+
+extern "C" int drt_cuda_analyse_scene(const drt_scene *scene, const drt_camera *camera, uint32_t width, uint32_t height,
+                                      uint32_t hit_rect_out[4], int32_t *boundary_out)
+{
+    if(!scene || !camera || !hit_rect_out || !boundary_out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    if(scene->num_surfaces < 0 || scene->num_surfaces > DRT_MAX_SURFACES) return fail(DRT_CUDA_E_ARG, "%d surfaces out of range", scene->num_surfaces);
+    double u0 = 0, u1 = 0, v0 = 0, v1 = 0;
+    bool have = scene_hit_bound(scene, camera, &u0, &u1, &v0, &v1);
+    hit_rect(have, u0, u1, v0, v1, width, height, hit_rect_out);
+    for(int i = 0; i < scene->num_surfaces; i += 1) boundary_out[i] = surface_is_boundary(scene, i) ? 1 : 0;
+    return DRT_CUDA_OK;
+}
+
 template <typename R>
 static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
 {
@@ -166,32 +268,6 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
         if(f->normal[a] != 1.0 && f->normal[a] != -1.0) return -1;
         return a;
     };
-    /* boundary plane: every other surface (rectangle corners, sphere extents, points) lies in one closed half-space of it */
-    auto is_boundary = [&](int i) -> bool {
-        const drt_surface *f = &s->surfaces[i];
-        if(f->type != DRT_GEO_PLANE) return false;
-        const double eps = 1e-6;   /* two orders below the reference's 1e-4 ray offset */
-        double lo = 0.0, hi = 0.0;
-        auto side = [&](const double *q, double r) {
-            double d = (q[0] - f->position[0]) * f->normal[0] + (q[1] - f->position[1]) * f->normal[1] + (q[2] - f->position[2]) * f->normal[2];
-            if(d - r < lo) lo = d - r;
-            if(d + r > hi) hi = d + r;
-        };
-        for(int j = 0; j < s->num_surfaces; j += 1)
-        {
-            if(j == i) continue;
-            const drt_surface *o = &s->surfaces[j];
-            if(o->type == DRT_GEO_PLANE)
-                for(int c = 0; c < 4; c += 1)
-                {
-                    double q[3];
-                    for(int k = 0; k < 3; k += 1) q[k] = o->position[k] + ((c & 1) ? o->u[k] : 0.0) + ((c & 2) ? o->v[k] : 0.0);
-                    side(q, 0.0);
-                }
-            else side(o->position, o->type == DRT_GEO_SPHERE ? o->radius : 0.0);
-        }
-        return lo >= -eps || hi <= eps;
-    };
     int slot = 0;
     for(int pass = 0; pass < 9; pass += 1)   /* passes 0-7: plane group (pass / 2), boundary planes first; pass 8: spheres */
         for(int i = 0; i < s->num_surfaces; i += 1)
@@ -201,7 +277,7 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
             if(pass < 8)
             {
                 if(f->type != DRT_GEO_PLANE || plane_axis(f) != (group < 3 ? group : -1)) continue;
-                if(is_boundary(i) != ((pass & 1) == 0)) continue;
+                if(surface_is_boundary(s, i) != ((pass & 1) == 0)) continue;
                 if((pass & 1) == 0) g->nax_b[group] += 1;
             }
             else if(f->type != DRT_GEO_SPHERE) continue;
@@ -287,53 +363,7 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     fill_geom(g32, scene, camera);
     fill_geom(g64, scene, camera);
 
-    /* Screen-space bound of the scene for a pinhole camera: the film point whose ray passes through a world point Q is
-     * P = ap + (ap - Q) * f / depth(Q) (sample_scene :602-607: the ray starts on the film and runs through the aperture), so the
-     * projection of a convex surface is the hull of its projected corners as long as every corner is in front of the aperture. */
-    ctx->hit_bound = false;
-    if(camera->aperture_radius == 0.0)
-    {
-        const double *ap = camera->aperture_position, *fw = camera->forward;
-        double fd = 0.0;
-        for(int k = 0; k < 3; k += 1) fd += (ap[k] - camera->film_bottom_left[k]) * fw[k];
-        double g_rr = 0.0, g_uu = 0.0, g_ru = 0.0;
-        for(int k = 0; k < 3; k += 1) { g_rr += camera->right[k] * camera->right[k]; g_uu += camera->up[k] * camera->up[k]; g_ru += camera->right[k] * camera->up[k]; }
-        const double g_det = g_rr * g_uu - g_ru * g_ru;
-        bool ok = fd > 0.0 && camera->pixel_width > 0.0 && camera->pixel_height > 0.0 && g_det > 1e-12;
-        double u0 = 1e300, u1 = -1e300, v0 = 1e300, v1 = -1e300;
-        auto project = [&](const double *q) {
-            double depth = 0.0;
-            for(int k = 0; k < 3; k += 1) depth += (q[k] - ap[k]) * fw[k];
-            if(!(depth > 1e-9)) { ok = false; return; }
-            double dr = 0.0, du = 0.0;   /* (P - film_bottom_left) = a * right + b * up: solve for a, b (no orthonormality assumed) */
-            for(int k = 0; k < 3; k += 1)
-            {
-                double pk = ap[k] + (ap[k] - q[k]) * (fd / depth) - camera->film_bottom_left[k];
-                dr += pk * camera->right[k]; du += pk * camera->up[k];
-            }
-            double u = (dr * g_uu - du * g_ru) / g_det / camera->pixel_width, v = (du * g_rr - dr * g_ru) / g_det / camera->pixel_height;
-            if(u < u0) u0 = u; if(u > u1) u1 = u; if(v < v0) v0 = v; if(v > v1) v1 = v;
-        };
-        for(int i = 0; i < scene->num_surfaces && ok; i += 1)
-        {
-            const drt_surface *f = &scene->surfaces[i];
-            if(f->type == DRT_GEO_PLANE)
-                for(int c = 0; c < 4; c += 1)
-                {
-                    double q[3];
-                    for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + ((c & 1) ? f->u[k] : 0.0) + ((c & 2) ? f->v[k] : 0.0);
-                    project(q);
-                }
-            else if(f->type == DRT_GEO_SPHERE)
-                for(int c = 0; c < 8; c += 1)   /* corners of the sphere's bounding cube */
-                {
-                    double q[3];
-                    for(int k = 0; k < 3; k += 1) q[k] = f->position[k] + (((c >> k) & 1) ? f->radius : -f->radius);
-                    project(q);
-                }
-        }
-        if(ok && u0 <= u1) { ctx->hit_bound = true; ctx->hit_u0 = u0; ctx->hit_u1 = u1; ctx->hit_v0 = v0; ctx->hit_v1 = v1; }
-    }
+    ctx->hit_bound = scene_hit_bound(scene, camera, &ctx->hit_u0, &ctx->hit_u1, &ctx->hit_v0, &ctx->hit_v1);
 
     /* spectrum pool: row 0 = zeros, then one row per SPD a material was given */
     SpdIndex index;
@@ -524,13 +554,9 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.pixels_per_task = spp >= 32 ? 1 : 32 / spp;
     for(int i = 0; i < scatter_count; i += 1) L.scatter[i] = FilmPtrs{ scatter[i].sum, scatter[i].filter, scatter[i].mean, scatter[i].m2 };
     L.scatter_count = (uint32_t)scatter_count; L.scatter_rank = (uint32_t)scatter_rank; L.scatter_slice = (uint32_t)scatter_slice;
-    L.hit_x0 = 0; L.hit_y0 = 0; L.hit_x1 = p->width; L.hit_y1 = p->height;
-    if(ctx->hit_bound)   /* one pixel of slack on every side: the f32 camera arithmetic of the kernel against this f64 projection */
-    {
-        auto clampi = [](double v, uint32_t hi) -> uint32_t { return v <= 0.0 ? 0u : v >= (double)hi ? hi : (uint32_t)v; };
-        L.hit_x0 = clampi(floor(ctx->hit_u0) - 1.0, p->width);  L.hit_x1 = clampi(ceil(ctx->hit_u1) + 1.0, p->width);
-        L.hit_y0 = clampi(floor(ctx->hit_v0) - 1.0, p->height); L.hit_y1 = clampi(ceil(ctx->hit_v1) + 1.0, p->height);
-    }
+    uint32_t rect[4];
+    hit_rect(ctx->hit_bound, ctx->hit_u0, ctx->hit_u1, ctx->hit_v0, ctx->hit_v1, p->width, p->height, rect);
+    L.hit_x0 = rect[0]; L.hit_y0 = rect[1]; L.hit_x1 = rect[2]; L.hit_y1 = rect[3];
     record_layout(ctx, p->max_depth, L);
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     int warps, ctas_per_sm;

@@ -63,6 +63,13 @@ def merge_distributed_(film, root=0, group=None):
     return 3
 
 
+def slice_partition(npix, world):
+    """Pixel slices of the scattered exchange: (slice, [(p0, p1) per rank]) with slice = ceil(npix / world); rank r owns
+    [r * slice, (r + 1) * slice) clipped to the image, so trailing ranks of a ragged image may own fewer pixels or none."""
+    per = -(-npix // world)
+    return per, [(min(npix, r * per), min(npix, (r + 1) * per)) for r in range(world)]
+
+
 class PeerFilmGroup:
     """The fused multi-GPU film exchange over peer memory.  Every rank owns a library-allocated STAGING film; all staging films,
     the root's merged film and the root's three BGRA images are mapped into every process through CUDA IPC once.
@@ -79,7 +86,7 @@ class PeerFilmGroup:
         self.ctx, self.width, self.height, self.root, self.group, self.scatter = ctx, width, height, root, group, scatter
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         npix = width * height
-        self.slice = -(-npix // self.world)                      # pixels per owner; staging holds world * slice pixels
+        self.slice, parts = slice_partition(npix, self.world)      # pixels per owner; staging holds world * slice pixels
         rows = -(-self.slice * self.world // width) if scatter else height
         self.mine = ctx.film_alloc(width, rows)
         self.merged = ctx.film_alloc(width, height) if self.rank == root else None
@@ -104,7 +111,7 @@ class PeerFilmGroup:
             self._opened.append(self.dst)
             self.img_base = ctx.buffer_ipc_open(rooted[0][1])
         if scatter:
-            self.p0, self.p1 = min(npix, self.rank * self.slice), min(npix, (self.rank + 1) * self.slice)
+            self.p0, self.p1 = parts[self.rank]
         else:
             self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
         self.bgra = [self.img_base + i * npix * 4 for i in range(3)]

@@ -102,6 +102,13 @@ int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params
  * specialisation, one-pixel-per-task shape), warps_per_cta and ctas_per_sm as launched for a film render with `params`. */
 int  drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_render_params *params, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm);
 
+/* The two exact cullings drt_cuda_upload_scene prepares, as plain host arithmetic (no device needed; used by the CPU-tier tests):
+ * hit_rect = {x0, y0, x1, y1}: pixels outside [x0, x1) x [y0, y1) of a width x height image cannot see any surface (pinhole camera;
+ * the whole image when no bound exists, e.g. a thin lens), so the kernel counts their camera paths instead of tracing them;
+ * boundary[i] = 1 for a plane that has the whole scene in one closed half-space: shadow rays do not test it. */
+int  drt_cuda_analyse_scene(const drt_scene *scene, const drt_camera *camera, uint32_t width, uint32_t height,
+                            uint32_t hit_rect[4], int32_t *boundary /* [scene->num_surfaces] */);
+
 /* Counters of the most recent render_* / sample_paths call (waits for it to finish). */
 int  drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out);
 

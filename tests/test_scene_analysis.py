@@ -1,0 +1,86 @@
+"""CPU tier: the host-side analyses behind the kernel's two exact cullings (drt_cuda_analyse_scene, plain arithmetic in
+libdrt_cuda.so, no device needed) and the slice arithmetic of the scattered multi-GPU exchange.
+
+* hit rectangle: every camera path of a pixel OUTSIDE it must end on the escape material at depth 0 -- checked by tracing those
+  pixels with the oracle (which knows nothing of the rectangle) at several samples per pixel and three image shapes;
+* boundary planes: the walls of the Cornell rooms are flagged, lights and objects inside are not."""
+import importlib
+
+import numpy as np
+import pytest
+
+import common
+import oracledriver
+
+cuda = importlib.import_module("daily-ray-trace_b200.cuda")
+film = importlib.import_module("daily-ray-trace_b200.film")
+
+SCENES = ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward", "first_scene", "example_scene", "stress_all"]
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (40, 56), (33, 33)])
+@pytest.mark.parametrize("name", SCENES)
+def test_pixels_outside_the_hit_rectangle_see_nothing(name, w, h):
+    spp, depth = 6, 4
+    cfg, tables, scene, camera = common.load(name, w, h, spp, depth)
+    (x0, y0, x1, y1), _ = cuda.analyse_scene(scene, camera, w, h)
+    assert 0 <= x0 <= x1 <= w and 0 <= y0 <= y1 <= h
+    prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 31)
+    strips = [(0, 0, w, y0), (0, y1, w, h), (0, y0, x0, y1), (x1, y0, w, y1)]      # below, above, left, right of the rectangle
+    outside = 0
+    for sx0, sy0, sx1, sy1 in strips:
+        if sx1 <= sx0 or sy1 <= sy0:
+            continue
+        total, _, _, _, cnt = oracledriver.render_tile(scene, camera, prm, sx0, sy0, sx1, sy1)
+        n = scene.num_wavelengths
+        outside += (sx1 - sx0) * (sy1 - sy0)
+        assert not total[:, :n].any(), (name, (sx0, sy0, sx1, sy1))
+        assert cnt.shaded_bounces == 0 and cnt.shadow_rays == 0 and cnt.closest_rays == cnt.paths == (sx1 - sx0) * (sy1 - sy0) * spp
+        assert cnt.terminated_at_depth[0] == cnt.paths
+    if name in ("init_cornell", "cornell_plane_light"):
+        assert outside >= 0.2 * w * h            # these two boxes fill only part of the frame: the bound must find that
+
+
+def test_thin_lens_has_no_bound():
+    cfg, tables, scene, camera = common.load("stress_all", 48, 36, 1, 4)      # the stress scene has aperture > 0
+    assert camera.aperture_radius > 0
+    rect, _ = cuda.analyse_scene(scene, camera, 48, 36)
+    assert rect == (0, 0, 48, 36)
+
+
+@pytest.mark.parametrize("name", ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward"])
+def test_room_walls_are_boundary_planes(name):
+    cfg, tables, scene, camera = common.load(name, 32, 32, 1, 4)
+    _, boundary = cuda.analyse_scene(scene, camera, 32, 32)
+    types = [scene.surfaces[i].type for i in range(scene.num_surfaces)]
+    planes = [i for i, t in enumerate(types) if t == 3]
+    assert sum(boundary) == 5, boundary                      # floor, ceiling, back and side walls
+    assert all(types[i] == 3 for i, b in enumerate(boundary) if b)
+    # brute force: a flagged plane has every other surface's corners / extents on one side, an unflagged plane does not
+    for i in planes:
+        f = scene.surfaces[i]
+        p, nrm = np.array(f.position[:]), np.array(f.normal[:])
+        lo = hi = 0.0
+        for j in range(scene.num_surfaces):
+            if j == i:
+                continue
+            o = scene.surfaces[j]
+            if o.type == 3:
+                pts = [np.array(o.position[:]) + a * np.array(o.u[:]) + b * np.array(o.v[:]) for a in (0, 1) for b in (0, 1)]
+                ds = [((q - p) @ nrm, 0.0) for q in pts]
+            else:
+                ds = [((np.array(o.position[:]) - p) @ nrm, o.radius if o.type == 2 else 0.0)]
+            for d, r in ds:
+                lo, hi = min(lo, d - r), max(hi, d + r)
+        assert boundary[i] == (lo >= -1e-6 or hi <= 1e-6), (name, i)
+
+
+@pytest.mark.parametrize("npix,world", [(1024 * 1024, 8), (37 * 23, 3), (5, 8), (4096 * 4096, 8), (640 * 480, 6)])
+def test_slice_partition_covers_every_pixel_once(npix, world):
+    per, parts = film.slice_partition(npix, world)
+    assert per * world >= npix and len(parts) == world
+    covered = np.zeros(npix, np.int32)
+    for p0, p1 in parts:
+        assert 0 <= p0 <= p1 <= npix and p1 - p0 <= per
+        covered[p0:p1] += 1
+    assert (covered == 1).all()
