@@ -18,6 +18,12 @@
  *
  * No path state ever goes to global memory; HBM traffic is the film write, so the kernel is bound by FP32 issue, not
  * by the 1.2 KB-per-bounce queue traffic of a global-memory wavefront.
+ *
+ * Template parameters: R = float (default) or double (branch-flip diagnostic) arithmetic of phase 1; NS = wavelength slots
+ * per half-warp lane (2, 3, 5, 8); ALLFAST = every surface material is a two-lobe plastic under one light (compact records,
+ * no general evaluators, 72 registers -> 2 CTAs x 14 warps per SM); PAIRED = one pixel per task (spp >= 32) or 32/spp pixels.
+ * Work the kernel proves unnecessary on the host's word (drt_capi.cu, exact): shadow rays do not test boundary planes
+ * (GeomT::nax_b), pixels outside the scene's screen-space bound are counted instead of traced (RenderLaunch::hit_*).
  * Quirk numbers (Qn) refer to SURVEY.md Appendix A; the CPU restatement of the same lines is oracle/drt_oracle.c.
  */
 #pragma once
