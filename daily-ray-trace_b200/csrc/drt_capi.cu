@@ -55,6 +55,7 @@ struct drt_cuda_context
     SpdIndex *d_index = nullptr;
     float *d_pool = nullptr;
     uint32_t pool_words = 0;
+    size_t pool_capacity = 0;
     void  *d_rgb_tables = nullptr;
     DeviceStats *d_stats = nullptr;
     unsigned int *d_counter = nullptr;
@@ -430,15 +431,19 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     std::vector<unsigned char> rgbt(drt_rgb_tables_bytes());
     drt_fill_rgb_tables(rgbt.data(), tables);
 
-    cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool); cudaFree(ctx->d_rgb_tables);
-    ctx->d_geom32 = ctx->d_geom64 = nullptr; ctx->d_index = nullptr; ctx->d_pool = nullptr; ctx->d_rgb_tables = nullptr;
+    /* the fixed-size blocks are allocated once per context; the pool only grows (a re-upload per frame costs five small copies) */
     ctx->have_scene = false;
     cudaError_t e = cudaSuccess;
-    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_geom32, sizeof(GeomT<float>));
-    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_geom64, sizeof(GeomT<double>));
-    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_index, sizeof(SpdIndex));
-    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_pool, pool.size() * 4);
-    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_rgb_tables, rgbt.size());
+    if(e == cudaSuccess && !ctx->d_geom32) e = cudaMalloc(&ctx->d_geom32, sizeof(GeomT<float>));
+    if(e == cudaSuccess && !ctx->d_geom64) e = cudaMalloc(&ctx->d_geom64, sizeof(GeomT<double>));
+    if(e == cudaSuccess && !ctx->d_index) e = cudaMalloc(&ctx->d_index, sizeof(SpdIndex));
+    if(e == cudaSuccess && !ctx->d_rgb_tables) e = cudaMalloc(&ctx->d_rgb_tables, rgbt.size());
+    if(e == cudaSuccess && ctx->pool_capacity < pool.size() * 4)
+    {
+        cudaFree(ctx->d_pool); ctx->d_pool = nullptr; ctx->pool_capacity = 0;
+        e = cudaMalloc(&ctx->d_pool, pool.size() * 4);
+        if(e == cudaSuccess) ctx->pool_capacity = pool.size() * 4;
+    }
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_geom32, g32, sizeof(GeomT<float>), cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_geom64, g64, sizeof(GeomT<double>), cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_index, &index, sizeof(index), cudaMemcpyHostToDevice);
@@ -618,9 +623,12 @@ extern "C" int drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_para
     float *base = ctx->d_film;
     FilmPtrs f = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
     /* Large frames are rendered in row bands so that the read-back of a finished band (PCIe) runs under the render of the
-     * next one: with pinned host buffers only the last band's copy is exposed.  Rows are contiguous in every plane. */
+     * next one: with pinned host buffers only the last (small) band's copy is exposed.  Rows are contiguous in every plane. */
     const uint64_t paths = (uint64_t)npix * (params->sample_end - params->sample_begin);
-    int bands = (paths >= (1ull << 26) && params->height >= 64) ? 8 : 1;
+    /* band boundaries in 1/16 of the image height: three quarters, then ever smaller bands, so that the copy left exposed
+     * after the last render is 1/16 of the film */
+    static const int cut[] = { 0, 4, 8, 12, 14, 15, 16 };
+    int bands = (paths >= (1ull << 26) && params->height >= 64) ? 6 : 1;
     if(bands > 1 && !ctx->band_render)
     {
         CU(cudaStreamCreateWithFlags(&ctx->band_render, cudaStreamNonBlocking));
@@ -632,7 +640,8 @@ extern "C" int drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_para
     const size_t n = (size_t)ctx->n, w = params->width;
     for(int b = 0; b < bands; b += 1)
     {
-        const uint32_t y0 = (uint32_t)((uint64_t)params->height * b / bands), y1 = (uint32_t)((uint64_t)params->height * (b + 1) / bands);
+        const uint32_t y0 = bands > 1 ? (uint32_t)((uint64_t)params->height * cut[b] / 16) : 0u;
+        const uint32_t y1 = bands > 1 ? (uint32_t)((uint64_t)params->height * cut[b + 1] / 16) : params->height;
         rc = launch(ctx, params, 0, y0, params->width, y1, f, nullptr, 0, sr, nullptr, nullptr, nullptr, 0, 0, 0, b > 0);
         if(rc != DRT_CUDA_OK) return rc;
         if(bands > 1) { CU(cudaEventRecord(ctx->band_done[b], sr)); CU(cudaStreamWaitEvent(sc, ctx->band_done[b], 0)); }
