@@ -31,6 +31,7 @@ CASES = [
     ("first_scene", 32, 32, (8, 8, 24, 24), 2, 4, "pixel_center", 15),
     ("example_scene", 32, 32, (8, 8, 24, 24), 1, 3, "pixel_random", 16),
     ("stress_all", 64, 48, (16, 8, 40, 24), 2, 6, "pixel_random", 17),
+    ("rotated_room", 64, 48, (20, 12, 44, 28), 2, 5, "pixel_random", 18),
 ]
 
 

@@ -19,6 +19,7 @@ CASES = [
     ("first_scene", 16, 16, 2, 4, "pixel_center"),
     ("example_scene", 16, 16, 1, 3, "pixel_random"),
     ("stress_all", 32, 24, 4, 6, "pixel_random"),
+    ("rotated_room", 32, 24, 3, 5, "pixel_random"),      # planes in general position, a tilted card and a ball inside, plane light
 ]
 
 

@@ -15,7 +15,8 @@ import oracledriver
 cuda = importlib.import_module("daily-ray-trace_b200.cuda")
 film = importlib.import_module("daily-ray-trace_b200.film")
 
-SCENES = ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward", "first_scene", "example_scene", "stress_all"]
+SCENES = ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward", "first_scene", "example_scene", "stress_all",
+          "rotated_room"]
 
 
 @pytest.mark.parametrize("w,h", [(64, 48), (40, 56), (33, 33)])
@@ -48,7 +49,7 @@ def test_thin_lens_has_no_bound():
     assert rect == (0, 0, 48, 36)
 
 
-@pytest.mark.parametrize("name", ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward"])
+@pytest.mark.parametrize("name", ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward", "rotated_room"])
 def test_room_walls_are_boundary_planes(name):
     cfg, tables, scene, camera = common.load(name, 32, 32, 1, 4)
     _, boundary = cuda.analyse_scene(scene, camera, 32, 32)
