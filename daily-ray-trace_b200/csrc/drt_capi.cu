@@ -904,6 +904,76 @@ extern "C" int drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film 
     return DRT_CUDA_OK;
 }
 
+/* One process, several devices: the scattered exchange of bench.py without IPC (all pointers live in one address space). */
+extern "C" int drt_cuda_render_host_multi(drt_cuda_context **ctxs, int count, const drt_render_params *params, const drt_film *out)
+{
+    if(!ctxs || count < 1 || count > DRT_MAX_PEERS || !params || !out || !out->sum || !out->filter || !out->mean || !out->m2)
+        return fail(DRT_CUDA_E_ARG, "bad argument (1..%d contexts)", DRT_MAX_PEERS);
+    for(int g = 0; g < count; g += 1)
+    {
+        if(!ctxs[g] || !ctxs[g]->have_scene) return fail(DRT_CUDA_E_STATE, "context %d has no scene", g);
+        if(ctxs[g]->n != ctxs[0]->n) return fail(DRT_CUDA_E_ARG, "context %d holds another scene", g);
+        for(int h = 0; h < g; h += 1) if(ctxs[h]->device == ctxs[g]->device) return fail(DRT_CUDA_E_ARG, "contexts %d and %d share device %d", h, g, ctxs[g]->device);
+    }
+    if(count == 1) return drt_cuda_render_host(ctxs[0], params, out);
+    const uint32_t spp = params->sample_end > params->sample_begin ? params->sample_end - params->sample_begin : 0;
+    if(spp < (uint32_t)count) return fail(DRT_CUDA_E_ARG, "%u samples per pixel cannot be split over %d devices", spp, count);
+    const size_t n = (size_t)ctxs[0]->n, npix = (size_t)params->width * params->height;
+    const uint64_t slice = (npix + (size_t)count - 1) / (size_t)count;
+    const uint32_t rows = (uint32_t)((slice * (uint64_t)count + params->width - 1) / params->width);
+
+    drt_film staging[DRT_MAX_PEERS];
+    memset(staging, 0, sizeof(staging));
+    drt_film merged;
+    memset(&merged, 0, sizeof(merged));
+    int rc = DRT_CUDA_OK;
+    /* peer access both ways, a staging film per device, the merged film on device 0 */
+    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
+    {
+        if(cudaSetDevice(ctxs[g]->device) != cudaSuccess) { rc = fail(DRT_CUDA_E_CUDA, "cudaSetDevice(%d)", ctxs[g]->device); break; }
+        for(int h = 0; h < count; h += 1)
+        {
+            if(h == g) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctxs[g]->device, ctxs[h]->device);
+            if(!can) { rc = fail(DRT_CUDA_E_UNSUPPORTED, "device %d cannot access device %d", ctxs[g]->device, ctxs[h]->device); break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[h]->device, 0);
+            if(e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if(e != cudaSuccess) { rc = fail(DRT_CUDA_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); break; }
+        }
+        if(rc == DRT_CUDA_OK) rc = drt_cuda_film_alloc(ctxs[g], params->width, rows, &staging[g]);
+    }
+    if(rc == DRT_CUDA_OK) rc = drt_cuda_film_alloc(ctxs[0], params->width, params->height, &merged);
+    /* every device renders its share of the samples of every pixel and stores finished pixels with their owner */
+    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
+    {
+        drt_render_params p = *params;
+        p.sample_begin = params->sample_begin + (uint32_t)((uint64_t)spp * g / count);
+        p.sample_end = params->sample_begin + (uint32_t)((uint64_t)spp * (g + 1) / count);
+        rc = drt_cuda_render_device_scatter(ctxs[g], &p, staging, count, g, slice, nullptr);
+    }
+    for(int g = 0; g < count; g += 1) { cudaSetDevice(ctxs[g]->device); if(cudaDeviceSynchronize() != cudaSuccess && rc == DRT_CUDA_OK) rc = fail(DRT_CUDA_E_CUDA, "render on device %d failed", ctxs[g]->device); }
+    /* every device merges its slice from local memory into the film on device 0 */
+    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
+    {
+        const uint64_t p0 = (uint64_t)g * slice < npix ? (uint64_t)g * slice : npix, p1 = (uint64_t)(g + 1) * slice < npix ? (uint64_t)(g + 1) * slice : npix;
+        rc = drt_cuda_film_merge_slices(ctxs[g], &merged, &staging[g], count, slice, params->width, params->height, p0, p1, nullptr, nullptr, nullptr, nullptr);
+    }
+    for(int g = 0; g < count; g += 1) { cudaSetDevice(ctxs[g]->device); if(cudaDeviceSynchronize() != cudaSuccess && rc == DRT_CUDA_OK) rc = fail(DRT_CUDA_E_CUDA, "merge on device %d failed", ctxs[g]->device); }
+    if(rc == DRT_CUDA_OK)
+    {
+        cudaSetDevice(ctxs[0]->device);
+        cudaError_t e = cudaMemcpy(out->sum, merged.sum, npix * n * 4, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(out->mean, merged.mean, npix * n * 4, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(out->m2, merged.m2, npix * n * 4, cudaMemcpyDeviceToHost);
+        if(e == cudaSuccess) e = cudaMemcpy(out->filter, merged.filter, npix * 4, cudaMemcpyDeviceToHost);
+        if(e != cudaSuccess) rc = fail(DRT_CUDA_E_CUDA, "film read-back: %s", cudaGetErrorString(e));
+    }
+    for(int g = 0; g < count; g += 1) if(staging[g].sum) drt_cuda_film_free(ctxs[g], &staging[g]);
+    if(merged.sum) drt_cuda_film_free(ctxs[0], &merged);
+    return rc;
+}
+
 extern "C" int drt_cuda_measure_fp32_peak(drt_cuda_context *ctx, int packed, double *tflops)
 {
     if(!ctx || !tflops) return fail(DRT_CUDA_E_ARG, "NULL argument");

@@ -13,7 +13,7 @@ from ._structs import Camera, RenderParams, Scene, Tables
 GEOMETRY_F32, GEOMETRY_F64 = 0, 1
 
 EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
-           "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host",
+           "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host", "drt_cuda_render_host_multi",
            "drt_cuda_get_stats", "drt_cuda_analyse_scene", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
@@ -63,6 +63,7 @@ def lib():
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
         L.drt_cuda_film_sizes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.drt_cuda_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_void_p]
+        L.drt_cuda_render_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.POINTER(Film)]
         L.drt_cuda_render_device_scatter.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_int, C.c_uint64, C.c_void_p]
         L.drt_cuda_film_merge_slices.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                                                  C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -242,6 +243,17 @@ class Context:
         v = C.c_double()
         _check(lib().drt_cuda_measure_fp32_peak(self._h, int(packed), C.byref(v)))
         return v.value
+
+
+def render_host_multi(contexts, params):
+    """render_host over several Context objects on distinct devices of this process: dict of numpy f32 arrays like Context.render_host."""
+    npix, n = params.width * params.height, contexts[0].n
+    out = {"sum": np.empty((npix, n), np.float32), "filter": np.empty(npix, np.float32),
+           "mean": np.empty((npix, n), np.float32), "m2": np.empty((npix, n), np.float32)}
+    film = Film(out["sum"].ctypes.data, out["filter"].ctypes.data, out["mean"].ctypes.data, out["m2"].ctypes.data)
+    handles = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    _check(lib().drt_cuda_render_host_multi(handles, len(contexts), C.byref(params), C.byref(film)))
+    return out
 
 
 def analyse_scene(scene, camera, width, height):

@@ -6,7 +6,8 @@
  * (win32_main.c:129-152).  The render itself goes through the C ABI of include/drt_cuda.h; the timed region is the
  * reference's render_timer scope (sampling + film accumulation, daily_ray_trace.c:709-752; file I/O excluded).
  *
- *   drt_raytrace [config.cfg] [--device N] [--seed S] [--strict] [--f64-geometry]
+ *   drt_raytrace [config.cfg] [--device N] [--gpus G] [--seed S] [--strict] [--f64-geometry]
+ * --gpus G renders on devices N .. N+G-1: the samples of every pixel are split over them (drt_cuda_render_host_multi).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,11 +39,12 @@ static int spd_to_bmp(const char *spd, const char *bmp, const drt_tables *t)
 int main(int argc, char **argv)
 {
     const char *config_path = "config.cfg";
-    int device = 0, flags = DRT_PARSE_LEGACY_COMPAT, precision = DRT_GEOMETRY_F32;
+    int device = 0, gpus = 1, flags = DRT_PARSE_LEGACY_COMPAT, precision = DRT_GEOMETRY_F32;
     unsigned long long seed = 0;
     for(int i = 1; i < argc; i += 1)
     {
         if(strcmp(argv[i], "--device") == 0 && i + 1 < argc) device = atoi(argv[++i]);
+        else if(strcmp(argv[i], "--gpus") == 0 && i + 1 < argc) gpus = atoi(argv[++i]);
         else if(strcmp(argv[i], "--seed") == 0 && i + 1 < argc) seed = strtoull(argv[++i], NULL, 0);
         else if(strcmp(argv[i], "--strict") == 0) flags = DRT_PARSE_STRICT;
         else if(strcmp(argv[i], "--f64-geometry") == 0) precision = DRT_GEOMETRY_F64;
@@ -63,10 +65,14 @@ int main(int argc, char **argv)
     if(drt_load_tables(&cfg, ".", &tables) != DRT_OK) return die_host("spectral tables");
     if(drt_load_scene_file(".", cfg.input_scene, &tables, flags, cfg.output_width, cfg.output_height, &scene, &camera) != DRT_OK) return die_host("scene");
 
-    drt_cuda_context *ctx = NULL;
-    if(drt_cuda_create(device, &ctx) != DRT_CUDA_OK) return die_cuda("cuda");
-    if(drt_cuda_upload_scene(ctx, &scene, &camera, &tables) != DRT_CUDA_OK) return die_cuda("upload");
-    drt_cuda_set_geometry_precision(ctx, precision);
+    if(gpus < 1 || gpus > 16) { fprintf(stderr, "ERROR: --gpus %d (1..16)\n", gpus); return 1; }
+    drt_cuda_context *ctxs[16] = { NULL };
+    for(int g = 0; g < gpus; g += 1)
+    {
+        if(drt_cuda_create(device + g, &ctxs[g]) != DRT_CUDA_OK) return die_cuda("cuda");
+        if(drt_cuda_upload_scene(ctxs[g], &scene, &camera, &tables) != DRT_CUDA_OK) return die_cuda("upload");
+        drt_cuda_set_geometry_precision(ctxs[g], precision);
+    }
 
     size_t npix = (size_t)cfg.output_width * cfg.output_height, n = (size_t)scene.num_wavelengths;
     drt_film film;
@@ -82,10 +88,16 @@ int main(int argc, char **argv)
 
     printf("Starting render...\n");
     double t0 = now_ms();
-    if(drt_cuda_render_host(ctx, &prm, &film) != DRT_CUDA_OK) return die_cuda("render");
+    if(drt_cuda_render_host_multi(ctxs, gpus, &prm, &film) != DRT_CUDA_OK) return die_cuda("render");
     double ms = now_ms() - t0;
     drt_cuda_stats st;
-    drt_cuda_get_stats(ctx, &st);
+    memset(&st, 0, sizeof(st));
+    for(int g = 0; g < gpus; g += 1)
+    {
+        drt_cuda_stats one;
+        if(drt_cuda_get_stats(ctxs[g], &one) != DRT_CUDA_OK) return die_cuda("stats");
+        st.paths += one.paths; st.closest_rays += one.closest_rays; st.shadow_rays += one.shadow_rays;
+    }
     printf("Avg sample time: %fms\n", ms / (double)cfg.num_pixel_samples);
     printf("Total render time: %fms\n", ms);
     printf("Camera paths: %llu (%.3f Mpaths/s), rays: %llu (%.3f Mrays/s)\n", (unsigned long long)st.paths, (double)st.paths / ms * 1e-3,
@@ -102,6 +114,6 @@ int main(int argc, char **argv)
     printf("Converted.\n");
 
     free(film.sum); free(film.mean); free(film.m2); free(film.filter);
-    drt_cuda_destroy(ctx);
+    for(int g = 0; g < gpus; g += 1) drt_cuda_destroy(ctxs[g]);
     return 0;
 }

@@ -97,6 +97,12 @@ int  drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_render_para
  * `film_host` (pinned or pageable) and waits.  This is the end-to-end call the Linux main uses. */
 int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_host);
 
+/* render_host on several devices of ONE process (what `drt_raytrace --gpus G` calls): contexts[g] live on distinct devices and hold
+ * the same scene; the samples [sample_begin, sample_end) are split evenly over them, every device renders its share of every pixel
+ * with drt_cuda_render_device_scatter (peer access is enabled between the devices), merges its pixel slice with
+ * drt_cuda_film_merge_slices into a film on contexts[0]'s device, and that film is copied to `film_host`.  count = 1 is render_host. */
+int  drt_cuda_render_host_multi(drt_cuda_context **contexts, int count, const drt_render_params *params, const drt_film *film_host);
+
 /* Which render kernel the uploaded scene and the geometry precision select, for logs and benchmark lines:
  * name = "drt::render_kernel<float,5,true,true>" style string (geometry type, wavelength slots per half-warp lane, all-plastic
  * specialisation, one-pixel-per-task shape), warps_per_cta and ctas_per_sm as launched for a film render with `params`. */

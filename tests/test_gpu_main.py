@@ -52,3 +52,30 @@ def test_linux_main_writes_reference_format(host, tmp_path, scene):
         expect = film["m2"].astype(np.float64) / peak
     same = (var == expect) | (np.isnan(var) & np.isnan(expect))
     assert same.all()
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_linux_main_on_several_gpus(host, tmp_path, gpus):
+    """`drt_raytrace --gpus G` (drt_cuda_render_host_multi: samples split over the devices of one process, scattered exchange without
+    IPC) writes the same films as the single-device run: identical sample sets, partial films merged in another order."""
+    import torch
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    root = refdriver.make_root(str(tmp_path), common.ASSETS)
+    w, h, spp, n = 37, 23, 96, 69
+    open(os.path.join(root, "config.cfg"), "w").write(host.make_config_text(scene="scenes\\cornell_plane_light.scn", width=w, height=h, spp=spp))
+
+    def run(args):
+        out = subprocess.run([BIN, "--seed", "5"] + args, cwd=root, check=True, capture_output=True, text=True).stdout
+        assert "Render complete." in out
+        raw = {k: open(os.path.join(root, "output", k + ".spd"), "rb").read() for k in ("output", "average", "variance")}
+        return (np.frombuffer(raw["output"][40:], dtype=np.float64).reshape(w * h, n + 1).copy(),
+                np.frombuffer(raw["average"][40:], dtype=np.float64).reshape(w * h, n).copy(), out)
+
+    one_sum, one_mean, _ = run([])
+    many_sum, many_mean, log = run(["--gpus", str(gpus)])
+    assert f"Camera paths: {w * h * spp} " in log
+    assert np.array_equal(many_sum[:, n], one_sum[:, n])
+    for a, b in ((many_sum[:, :n], one_sum[:, :n]), (many_mean, one_mean)):
+        floor = 1e-5 * np.abs(b).max()
+        assert (np.abs(a - b) / np.maximum(np.abs(b), floor)).max() < 2e-4
