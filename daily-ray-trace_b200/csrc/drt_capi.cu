@@ -40,6 +40,8 @@ static int fail(int code, const char *fmt, ...)
 
 #define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while(0)
 
+#define DRT_RING 64
+
 struct drt_cuda_context
 {
     int    device = 0;
@@ -57,8 +59,15 @@ struct drt_cuda_context
     uint32_t pool_words = 0;
     size_t pool_capacity = 0;
     void  *d_rgb_tables = nullptr;
-    DeviceStats *d_stats = nullptr;
-    unsigned int *d_counter = nullptr;
+    /* Work counters and the task counter are PER CALL, taken round-robin from two small rings, so that renders of one context that
+     * are in flight on different streams (a user stream, render_host's band streams, the legacy stream of sample_paths) never
+     * share a counter: stats_ring[i] belongs to the i-th most recent render call (the bands of one render_host call share one),
+     * counter_ring[i] to one kernel launch.  A slot is reused after DRT_RING calls; get_stats reads the latest call's block.
+     * (The library's growing buffers d_film / d_dump / d_slice are reallocated with cudaFree, which waits for the device.) */
+    DeviceStats *d_stats_ring = nullptr;
+    unsigned int *d_counter_ring = nullptr;
+    uint64_t stats_calls = 0, counter_launches = 0;
+    DeviceStats *d_stats = nullptr;       /* the current call's block inside d_stats_ring */
     /* library-owned film + dump buffers for the host-buffer entry points */
     float *d_film = nullptr; size_t film_bytes = 0;
     float *d_dump = nullptr; size_t dump_bytes = 0;
@@ -93,8 +102,16 @@ extern "C" int drt_cuda_create(int device, drt_cuda_context **out)
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    CU(cudaMalloc(&ctx->d_stats, sizeof(DeviceStats)));
-    CU(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+    cudaError_t e = cudaMalloc(&ctx->d_stats_ring, DRT_RING * sizeof(DeviceStats));
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_counter_ring, DRT_RING * sizeof(unsigned int));
+    if(e == cudaSuccess) e = cudaMemset(ctx->d_stats_ring, 0, DRT_RING * sizeof(DeviceStats));
+    if(e != cudaSuccess)
+    {
+        cudaFree(ctx->d_stats_ring); cudaFree(ctx->d_counter_ring);
+        delete ctx;
+        return fail(DRT_CUDA_E_CUDA, "drt_cuda_create: %s", cudaGetErrorString(e));
+    }
+    ctx->d_stats = ctx->d_stats_ring;
     *out = ctx;
     return DRT_CUDA_OK;
 }
@@ -104,7 +121,7 @@ extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
-    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats); cudaFree(ctx->d_counter); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice);
+    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats_ring); cudaFree(ctx->d_counter_ring); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice);
     if(ctx->band_render) cudaStreamDestroy(ctx->band_render);
     if(ctx->band_copy) cudaStreamDestroy(ctx->band_copy);
     for(int i = 0; i < 16; i += 1) if(ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
@@ -122,10 +139,14 @@ static double value_at_wl(const drt_scene *s, const double *spd, double wl)
 /* Screen-space bound of the scene for a pinhole camera: the film point whose ray passes through a world point Q is
  * P = ap + (ap - Q) * f / depth(Q) (sample_scene :602-607: the ray starts on the film and runs through the aperture), so the
  * projection of a convex surface is the hull of its projected corners as long as every corner is in front of the aperture.
- * Returns false (no bound) for a thin lens or when a surface reaches behind the aperture.  Pure host arithmetic. */
+ * Returns false (no bound) for a thin lens, when a surface reaches behind the aperture, or when the escape material is
+ * EMISSIVE (an environment light, Q19: init_scene forces the escape material black-body, daily_ray_trace.c:148, and cast_ray
+ * :452-456 adds throughput * emission for a ray that leaves the scene -- such a pixel is lit although it sees no surface).
+ * Pure host arithmetic. */
 static bool scene_hit_bound(const drt_scene *scene, const drt_camera *camera, double *out_u0, double *out_u1, double *out_v0, double *out_v1)
 {
     if(camera->aperture_radius != 0.0) return false;
+    if(scene->escape_material >= 0 && scene->escape_material < scene->num_materials && scene->materials[scene->escape_material].is_emissive) return false;
     const double *ap = camera->aperture_position, *fw = camera->forward;
     double fd = 0.0;
     for(int k = 0; k < 3; k += 1) fd += (ap[k] - camera->film_bottom_left[k]) * fw[k];
@@ -345,19 +366,53 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
     for(int k = 0; k < 9; k += 1) g->lens_rot[k] = (R)c->lens_rotation[k];
 }
 
-extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables)
+/* Everything the kernels index device tables with, checked on the host (no device needed): a caller other than the in-repo
+ * parser gets an error code, not a wild shared-memory read. */
+extern "C" int drt_cuda_validate_scene(const drt_scene *scene)
 {
-    if(!ctx || !scene || !camera || !tables) return fail(DRT_CUDA_E_ARG, "NULL argument");
-    CU(cudaSetDevice(ctx->device));
+    if(!scene) return fail(DRT_CUDA_E_ARG, "NULL argument");
     int n = scene->num_wavelengths;
     if(n < 2 || n > DRT_MAX_WAVELENGTHS) return fail(DRT_CUDA_E_ARG, "%d wavelengths (need 2..%d)", n, DRT_MAX_WAVELENGTHS);
     if(scene->num_surfaces < 0 || scene->num_surfaces > DRT_MAX_SURFACES || scene->num_materials < 1 || scene->num_materials > DRT_MAX_MATERIALS)
         return fail(DRT_CUDA_E_ARG, "%d surfaces / %d materials out of range", scene->num_surfaces, scene->num_materials);
     if(scene->base_material < 0 || scene->escape_material < 0) return fail(DRT_CUDA_E_UNSUPPORTED, "scene needs a base_material and an escape_material");
+    if(scene->base_material >= scene->num_materials || scene->escape_material >= scene->num_materials)
+        return fail(DRT_CUDA_E_ARG, "base_material %d / escape_material %d out of range (%d materials)", scene->base_material, scene->escape_material, scene->num_materials);
+    if(!(scene->wl_interval > 0.0)) return fail(DRT_CUDA_E_ARG, "wl_interval must be positive");
     uint32_t i0 = (uint32_t)((DRT_TRANS_WL - scene->min_wl) / scene->wl_interval);
     if(DRT_TRANS_WL < scene->min_wl || (int)i0 + 1 >= n) return fail(DRT_CUDA_E_UNSUPPORTED, "630 nm (trans_wl, daily_ray_trace.c:381) lies outside the wavelength grid");
     for(int i = 0; i < scene->num_surfaces; i += 1)
+    {
         if(scene->surfaces[i].material < 0 || scene->surfaces[i].material >= scene->num_materials) return fail(DRT_CUDA_E_ARG, "surface %d: bad material index", i);
+        if(scene->surfaces[i].type < DRT_GEO_NONE || scene->surfaces[i].type > DRT_GEO_PLANE) return fail(DRT_CUDA_E_ARG, "surface %d: bad type %d", i, scene->surfaces[i].type);
+    }
+    for(int m = 0; m < scene->num_materials; m += 1)
+    {
+        const drt_material *mm = &scene->materials[m];
+        if(mm->num_lobes < 0 || mm->num_lobes > DRT_MAX_LOBES) return fail(DRT_CUDA_E_ARG, "material %d: %d lobes (0..%d)", m, mm->num_lobes, DRT_MAX_LOBES);
+        if(mm->dir_func < DRT_DIR_NONE || mm->dir_func >= DRT_DIR_COUNT) return fail(DRT_CUDA_E_ARG, "material %d: bad dir_func %d", m, mm->dir_func);
+        for(int k = 0; k < mm->num_lobes; k += 1)
+            if(mm->lobes[k] < -1 || mm->lobes[k] >= DRT_LOBE_COUNT) return fail(DRT_CUDA_E_ARG, "material %d: bad lobe id %d", m, mm->lobes[k]);
+    }
+    /* a surface that can be hit and shaded needs a direction sampler (the reference calls a NULL pointer there, daily_ray_trace.c:465) */
+    for(int i = 0; i < scene->num_surfaces; i += 1)
+    {
+        const drt_material *mm = &scene->materials[scene->surfaces[i].material];
+        if(scene->surfaces[i].type != DRT_GEO_POINT && scene->surfaces[i].type != DRT_GEO_NONE && !mm->is_black_body && mm->dir_func == DRT_DIR_NONE)
+            return fail(DRT_CUDA_E_ARG, "surface %d: its material has no dir_func", i);
+    }
+    return DRT_CUDA_OK;
+}
+
+extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables)
+{
+    if(!ctx || !scene || !camera || !tables) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    int vrc = drt_cuda_validate_scene(scene);
+    if(vrc != DRT_CUDA_OK) return vrc;
+    CU(cudaSetDevice(ctx->device));
+    const int n = scene->num_wavelengths;
+    const uint32_t i0 = (uint32_t)((DRT_TRANS_WL - scene->min_wl) / scene->wl_interval);
+    (void)i0;
 
     GeomT<float> *g32 = new GeomT<float>();
     GeomT<double> *g64 = new GeomT<double>();
@@ -551,7 +606,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     memset(&L, 0, sizeof(L));
     L.geom = ctx->f64_geometry ? ctx->d_geom64 : ctx->d_geom32;
     L.spd_index = ctx->d_index; L.pool = ctx->d_pool; L.pool_words = ctx->pool_words;
-    L.film = film; L.path_dump = dump; L.record_dump = record_dump; L.stats = ctx->d_stats; L.task_counter = ctx->d_counter;
+    L.film = film; L.path_dump = dump; L.record_dump = record_dump;
     L.width = p->width; L.height = p->height; L.x0 = x0; L.y0 = y0; L.x1 = x1; L.y1 = y1;
     L.sample_begin = p->sample_begin; L.sample_end = p->sample_end; L.max_depth = p->max_depth;
     L.pixel_scheme = p->pixel_scheme; L.seed = p->seed; L.accumulate = accumulate; L.nlights = ctx->nlights;
@@ -575,8 +630,14 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
     uint64_t need = (ntasks + warps - 1) / warps;
     if(grid > need) grid = need;
-    if(!keep_stats) CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
-    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned int), stream));
+    if(!keep_stats)
+    {
+        ctx->d_stats = ctx->d_stats_ring + (ctx->stats_calls++ % DRT_RING);
+        CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
+    }
+    L.stats = ctx->d_stats;
+    L.task_counter = ctx->d_counter_ring + (ctx->counter_launches++ % DRT_RING);
+    CU(cudaMemsetAsync(L.task_counter, 0, sizeof(unsigned int), stream));
     cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->all_fast, ctx->nslots, (int)grid, warps, smem, stream);
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
@@ -719,7 +780,9 @@ extern "C" int drt_cuda_film_to_rgb(drt_cuda_context *ctx, const drt_film *film,
     const float *plane = which == 0 ? film->sum : which == 1 ? film->mean : film->m2;
     const float *filter = which == 0 ? film->filter : nullptr;
     if(!plane || (which == 0 && !filter)) return fail(DRT_CUDA_E_ARG, "film plane is NULL");
-    uint32_t npix = width * height;
+    const uint64_t npix64 = (uint64_t)width * height;
+    if(npix64 == 0 || npix64 > 0xffffffffull) return fail(DRT_CUDA_E_ARG, "%u x %u pixels out of range", width, height);
+    uint32_t npix = (uint32_t)npix64;
     int grid = ctx->num_sms * 8;
     drt_launch_film_to_rgb(ctx->d_rgb_tables, plane, filter, which == 2, npix, rgb_device, bgra_device, grid, (cudaStream_t)stream);
     CU(cudaGetLastError());
@@ -746,8 +809,20 @@ extern "C" int drt_cuda_film_alloc(drt_cuda_context *ctx, uint32_t width, uint32
     CU(cudaSetDevice(ctx->device));
     size_t npix = (size_t)width * height, plane = npix * (size_t)ctx->n * 4;
     memset(out, 0, sizeof(*out));
-    CU(cudaMalloc(&out->sum, plane)); CU(cudaMalloc(&out->mean, plane)); CU(cudaMalloc(&out->m2, plane)); CU(cudaMalloc(&out->filter, npix * 4));
-    CU(cudaMemset(out->sum, 0, plane)); CU(cudaMemset(out->mean, 0, plane)); CU(cudaMemset(out->m2, 0, plane)); CU(cudaMemset(out->filter, 0, npix * 4));
+    cudaError_t e = cudaMalloc(&out->sum, plane);
+    if(e == cudaSuccess) e = cudaMalloc(&out->mean, plane);
+    if(e == cudaSuccess) e = cudaMalloc(&out->m2, plane);
+    if(e == cudaSuccess) e = cudaMalloc(&out->filter, npix * 4);
+    if(e == cudaSuccess) e = cudaMemset(out->sum, 0, plane);
+    if(e == cudaSuccess) e = cudaMemset(out->mean, 0, plane);
+    if(e == cudaSuccess) e = cudaMemset(out->m2, 0, plane);
+    if(e == cudaSuccess) e = cudaMemset(out->filter, 0, npix * 4);
+    if(e != cudaSuccess)
+    {
+        cudaFree(out->sum); cudaFree(out->mean); cudaFree(out->m2); cudaFree(out->filter);
+        memset(out, 0, sizeof(*out));
+        return fail(DRT_CUDA_E_CUDA, "film_alloc %ux%u: %s", width, height, cudaGetErrorString(e));
+    }
     return DRT_CUDA_OK;
 }
 
@@ -979,24 +1054,29 @@ extern "C" int drt_cuda_measure_fp32_peak(drt_cuda_context *ctx, int packed, dou
     if(!ctx || !tflops) return fail(DRT_CUDA_E_ARG, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     float *d_out = nullptr;
-    CU(cudaMalloc(&d_out, 4));
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, 4);
+    if(e == cudaSuccess) e = cudaEventCreate(&a);
+    if(e == cudaSuccess) e = cudaEventCreate(&b);
     const int iters = 4096, grid = ctx->num_sms * 8;
     double best = 0.0;
-    for(int rep = 0; rep < 5; rep += 1)
+    for(int rep = 0; rep < 5 && e == cudaSuccess; rep += 1)
     {
-        CU(cudaEventRecord(a, 0));
+        e = cudaEventRecord(a, 0);
         drt_launch_fma_peak(packed, d_out, iters, grid, 0);
-        CU(cudaEventRecord(b, 0));
-        CU(cudaEventSynchronize(b));
+        if(e == cudaSuccess) e = cudaEventRecord(b, 0);
+        if(e == cudaSuccess) e = cudaEventSynchronize(b);
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, a, b));
+        if(e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+        if(e != cudaSuccess) break;
         double flops = (double)grid * 256.0 * (double)iters * 16.0 * 2.0;
         double t = flops / (ms * 1e-3) / 1e12;
         if(rep > 0 && t > best) best = t;
     }
-    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d_out);
+    if(a) cudaEventDestroy(a);
+    if(b) cudaEventDestroy(b);
+    cudaFree(d_out);
+    if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "fp32 peak probe: %s", cudaGetErrorString(e));
     *tflops = best;
     return DRT_CUDA_OK;
 }

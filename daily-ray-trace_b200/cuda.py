@@ -14,7 +14,7 @@ GEOMETRY_F32, GEOMETRY_F64 = 0, 1
 
 EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "drt_cuda_destroy", "drt_cuda_upload_scene",
            "drt_cuda_scene_upload_bytes", "drt_cuda_set_geometry_precision", "drt_cuda_film_sizes", "drt_cuda_render_device", "drt_cuda_render_host", "drt_cuda_render_host_multi",
-           "drt_cuda_get_stats", "drt_cuda_analyse_scene", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
+           "drt_cuda_get_stats", "drt_cuda_analyse_scene", "drt_cuda_validate_scene", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
            "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close"]
@@ -58,6 +58,7 @@ def lib():
         L.drt_cuda_destroy.restype = None
         L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
         L.drt_cuda_scene_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        L.drt_cuda_validate_scene.argtypes = [C.POINTER(Scene)]
         L.drt_cuda_analyse_scene.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_int32)]
         L.drt_cuda_render_kernel_info.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
@@ -254,6 +255,11 @@ def render_host_multi(contexts, params):
     handles = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
     _check(lib().drt_cuda_render_host_multi(handles, len(contexts), C.byref(params), C.byref(film)))
     return out
+
+
+def validate_scene(scene):
+    """Raises CudaError for a scene drt_cuda_upload_scene would reject (host arithmetic, no device needed)."""
+    _check(lib().drt_cuda_validate_scene(C.byref(scene)))
 
 
 def analyse_scene(scene, camera, width, height):

@@ -69,6 +69,11 @@ void drt_cuda_destroy(drt_cuda_context *ctx);
 /* Copies scene, camera and tables to the device (f64 narrowed as the kernels need). */
 int  drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *scene, const drt_camera *camera, const drt_tables *tables);
 
+/* The checks upload_scene applies to a scene before anything reaches the device, as plain host arithmetic (no device needed):
+ * counts, material indices of surfaces / base / escape, lobe counts and ids, sampler ids, surface types, 630 nm inside the
+ * wavelength grid.  DRT_CUDA_E_ARG / DRT_CUDA_E_UNSUPPORTED with a message, or DRT_CUDA_OK. */
+int  drt_cuda_validate_scene(const drt_scene *scene);
+
 /* Bytes the last upload_scene copied host -> device. */
 int  drt_cuda_scene_upload_bytes(const drt_cuda_context *ctx, size_t *bytes);
 

@@ -32,12 +32,17 @@ CASES = [
     ("example_scene", 32, 32, (8, 8, 24, 24), 1, 3, "pixel_random", 16),
     ("stress_all", 64, 48, (16, 8, 40, 24), 2, 6, "pixel_random", 17),
     ("rotated_room", 64, 48, (20, 12, 44, 28), 2, 5, "pixel_random", 18),
+    # pinhole camera + EMISSIVE escape material (Q19 environment light): the tile straddles the scene's screen-space edge
+    ("sky_cornell", 64, 48, (0, 8, 24, 24), 2, 4, "pixel_random", 19),
 ]
 
 
 def main():
     assert refdriver.available(), "build oracle/_ref first (make -C oracle ref)"
+    only = set(sys.argv[1:])
     for name, w, h, tile, spp, depth, scheme, seed in CASES:
+        if only and name not in only:
+            continue
         parsed = host.parse_scene_text(open(common.scene_path(name)).read())
         upgraded = host.scene_to_text(parsed)
         with tempfile.TemporaryDirectory() as root:

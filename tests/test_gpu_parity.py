@@ -27,6 +27,7 @@ CASES = [
     ("example_scene", 32, 32, (0, 0, 32, 32), 1, 3, "pixel_random"),
     ("stress_all", 64, 48, (0, 0, 64, 48), 5, 6, "pixel_random"),
     ("rotated_room", 64, 48, (0, 0, 64, 48), 4, 5, "pixel_random"),     # all-plastic kernel on planes in general position
+    ("sky_cornell", 64, 48, (0, 0, 64, 48), 3, 4, "pixel_random"),      # pinhole + emissive escape material (Q19): no pixel may be culled
 ]
 
 
@@ -96,7 +97,8 @@ def test_film_matches_oracle(ctx):
 
 
 @pytest.mark.parametrize("scene,w,h,spp", [("init_cornell", 64, 48, 33), ("init_cornell", 40, 56, 5), ("cornell_downward", 48, 48, 32),
-                                           ("first_scene", 40, 30, 34), ("rotated_room", 56, 40, 32), ("rotated_room", 33, 41, 7)])
+                                           ("first_scene", 40, 30, 34), ("rotated_room", 56, 40, 32), ("rotated_room", 33, 41, 7),
+                                           ("sky_cornell", 64, 48, 33), ("sky_cornell", 40, 56, 5)])
 def test_full_frame_with_unseen_pixels(ctx, scene, w, h, spp):
     """Whole frames of scenes that fill only part of the image: pixels outside the screen-space bound of the scene are counted, not
     traced (RenderLaunch::hit_*), in both task shapes.  The film and every work counter must equal the oracle's, which traces them."""
@@ -112,6 +114,8 @@ def test_full_frame_with_unseen_pixels(ctx, scene, w, h, spp):
     assert np.array_equal(film["filter"], o_sum[:, n].astype(np.float32))
     lit_ref, lit_gpu = np.abs(o_sum[:, :n]).max(axis=1) > 0, np.abs(film["sum"]).max(axis=1) > 0
     print(f"\n{scene} {w}x{h}x{spp}: {100 * (1 - lit_ref.mean()):.1f} % of the pixels see nothing")
+    if scene == "sky_cornell":      # the sky lights every pixel, also those that see no surface (31 % of this frame)
+        assert lit_ref.all()
     assert np.array_equal(lit_ref, lit_gpu)                      # no pixel that receives light was skipped, none was invented
     bad = np.zeros(w * h, bool)
     for name, ref in (("sum", o_sum[:, :n]), ("mean", o_avg), ("m2", o_m2)):

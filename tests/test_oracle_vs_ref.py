@@ -20,6 +20,7 @@ CASES = [
     ("example_scene", 16, 16, 1, 3, "pixel_random"),
     ("stress_all", 32, 24, 4, 6, "pixel_random"),
     ("rotated_room", 32, 24, 3, 5, "pixel_random"),      # planes in general position, a tilted card and a ball inside, plane light
+    ("sky_cornell", 32, 24, 3, 4, "pixel_random"),       # pinhole camera + emissive escape material (Q19), all-plastic walls
 ]
 
 

@@ -42,6 +42,79 @@ def test_pixels_outside_the_hit_rectangle_see_nothing(name, w, h):
         assert outside >= 0.2 * w * h            # these two boxes fill only part of the frame: the bound must find that
 
 
+def test_emissive_escape_material_has_no_bound():
+    """Q19: an emissive escape material is an environment light (init_scene forces it black-body, daily_ray_trace.c:148; cast_ray
+    :452-456 adds throughput * emission when a ray leaves the scene), so pixels that see no surface are LIT: no pixel may be culled.
+    sky_cornell = init_cornell with a sky; without the sky the same camera gets a proper rectangle."""
+    w, h, spp = 64, 48, 2
+    cfg, tables, scene, camera = common.load("sky_cornell", w, h, spp, 4)
+    assert camera.aperture_radius == 0 and scene.materials[scene.escape_material].is_emissive
+    rect, _ = cuda.analyse_scene(scene, camera, w, h)
+    assert rect == (0, 0, w, h)
+    # the oracle (bit-exact with the reference) finds light in the frame's corners, which see no surface at all
+    prm = oracledriver.params(w, h, 0, spp, 4, cfg.pixel_scheme, 3)
+    total, _, _, _, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, 4, 4)
+    n = scene.num_wavelengths
+    assert (total[:, :n] > 0).all() and cnt.shaded_bounces == 0
+    scene.materials[scene.escape_material].is_emissive = 0
+    rect, _ = cuda.analyse_scene(scene, camera, w, h)
+    assert rect != (0, 0, w, h) and rect[0] > 4
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (33, 33)])
+@pytest.mark.parametrize("name", SCENES + ["sky_cornell"])
+def test_nothing_lit_outside_the_hit_rectangle(name, w, h):
+    """The culling's actual claim, stated on the result: no pixel outside the rectangle receives ANY radiance in the oracle's film
+    (zero shaded bounces is not enough when the escape material emits)."""
+    spp = 3
+    cfg, tables, scene, camera = common.load(name, w, h, spp, 4)
+    (x0, y0, x1, y1), _ = cuda.analyse_scene(scene, camera, w, h)
+    prm = oracledriver.params(w, h, 0, spp, 4, cfg.pixel_scheme, 77)
+    total, _, _, _, _ = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h)
+    n = scene.num_wavelengths
+    lit = (np.abs(total[:, :n]).max(axis=1) > 0).reshape(h, w)
+    inside = np.zeros((h, w), bool)
+    inside[y0:y1, x0:x1] = True
+    assert not (lit & ~inside).any(), (name, int((lit & ~inside).sum()))
+
+
+def _copy_scene(scene):
+    import ctypes as C
+    out = type(scene)()
+    C.memmove(C.byref(out), C.byref(scene), C.sizeof(scene))
+    return out
+
+
+def test_validate_scene_rejects_what_the_kernels_would_misindex():
+    """drt_cuda_upload_scene is a public entry point; counts and ids that index device tables are range-checked
+    (drt_cuda_validate_scene is the same check without a device)."""
+    cfg, tables, scene, camera = common.load("cornell_plane_light", 16, 16, 1, 4)
+    cuda.validate_scene(scene)
+
+    def bad(mutate, code=-103):
+        s = _copy_scene(scene)
+        mutate(s)
+        with pytest.raises(cuda.CudaError) as e:
+            cuda.validate_scene(s)
+        assert e.value.code == code, e.value
+
+    def set_lobes(s): s.materials[2].num_lobes = 17
+    def set_lobe_id(s): s.materials[2].lobes[0] = 7
+    def set_dir(s): s.materials[2].dir_func = 6
+    def set_base(s): s.base_material = s.num_materials
+    def set_escape(s): s.escape_material = 40
+    def set_type(s): s.surfaces[0].type = 9
+    def set_mat(s): s.surfaces[1].material = -2
+    def set_n(s): s.num_wavelengths = 1
+    def set_nsurf(s): s.num_surfaces = 17
+    def no_base(s): s.base_material = -1
+    def grid(s): s.min_wl = 700.0
+    for m in (set_lobes, set_lobe_id, set_dir, set_base, set_escape, set_type, set_mat, set_n, set_nsurf):
+        bad(m)
+    bad(no_base, -104)
+    bad(grid, -104)
+
+
 def test_thin_lens_has_no_bound():
     cfg, tables, scene, camera = common.load("stress_all", 48, 36, 1, 4)      # the stress scene has aperture > 0
     assert camera.aperture_radius > 0
