@@ -4,10 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            one rank per GPU (torchrun for N > 1)
     python bench.py --impl reference ...                           the reference's own CPU code on the host cores
 
-One "step" is one complete render of the workload: every pixel, `spp` samples per pixel per GPU, film accumulated, and
-(N > 1) the per-GPU films combined over NCCL.  Default workload = BASELINE.json configs[1]: init_cornell.scn,
-1024x1024, 1024 spp, max_cast_depth 4, pixel_random.  Scaling is WEAK: every GPU renders `spp` samples of every pixel
-(global sample indices [rank*spp, (rank+1)*spp)), so N GPUs deliver an N*spp image.
+One "step" is one complete render of the workload: every pixel, all its samples, film accumulated, and (N > 1) the
+per-GPU films combined.  Default workload = BASELINE.json configs[1] / the north-star target: init_cornell.scn, 1024x1024,
+1024 spp, max_cast_depth 4, pixel_random.  Scaling is STRONG by default: the 1024 samples of every pixel are split over the
+GPUs by sample index (rank r renders global samples [r*spp/N, (r+1)*spp/N)); --scaling weak gives every GPU `spp` samples
+(an N*spp image); the other mode is measured too and reported under its own key.  For every N the film that the end-to-end
+leg reads back is checked on a tile against the reference's own code over the same global sample indices (image_rmse).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -49,14 +51,26 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--geometry", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--merge", default="scatter", choices=["scatter", "p2p", "nccl"],
-                    help="multi-GPU film combination: render kernel scatters finished pixels to their owner over NVLink + local merge "
-                         "(default), gather-merge kernel over peer memory, or NCCL collectives")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = --spp samples per pixel IN TOTAL, spp/N per GPU (the north-star workload, default); "
+                         "weak = --spp samples per pixel PER GPU (an N*spp image).  The other mode is reported as an extra key.")
+    ap.add_argument("--merge", default="sharded", choices=["sharded", "nccl"],
+                    help="multi-GPU film combination: sharded = render kernel scatters finished pixels to their owner over NVLink, "
+                         "device-side flags, local merge, film stays sharded (default); nccl = 2 all_reduce + 1 reduce")
     return ap.parse_args()
 
 
+def samples(a, world):
+    """(samples per pixel in total, per GPU) of the chosen scaling mode"""
+    if a.scaling == "weak":
+        return a.spp * world, a.spp
+    return a.spp, max(1, a.spp // world)
+
+
 def workload_name(a):
-    return f"{a.scene}.scn {a.width}x{a.height} @{a.spp}spp/GPU depth{a.depth} pixel_random, N=69 wavelengths"
+    total, per = samples(a, max(1, a.gpus))
+    split = "" if a.gpus <= 1 else f" ({a.scaling} scaling: {per} spp on each of {a.gpus} GPUs, sample-index sharded)"
+    return f"{a.scene}.scn {a.width}x{a.height} @{total}spp depth{a.depth} pixel_random, N=69 wavelengths{split}"
 
 
 # ----------------------------------------------------------------------------------------------- CPU arms
@@ -122,6 +136,17 @@ def _cpu_worker_tile(job):
     return od.render_tile(sc, cam, prm, x0, y0, x1, y1, want_paths=True)[3]
 
 
+def _cpu_worker_tile_film(job):
+    """Film (sum, mean, M2) of a pixel rectangle over samples [s0, s1) through the reference's sample_scene."""
+    x0, y0, x1, y1, s0, s1 = job
+    w, h = _W["dims"]
+    if _W["kind"] == "reference":
+        return _W["ref"].render_tile(x0, y0, x1, y1, s0, s1)[:3]
+    od, sc, cam, cfg = _W["oracle"]
+    prm = od.params(w, h, s0, s1, _W["depth"], cfg.pixel_scheme, _W["seed"])
+    return od.render_tile(sc, cam, prm, x0, y0, x1, y1)[:3]
+
+
 class CpuArm:
     """The reference's CPU implementation of the path on all host cores: one single-threaded process per core (the
     reference has global RNG/scratch state), rows of the image split between them."""
@@ -150,6 +175,14 @@ class CpuArm:
         rows = self.pool.map(_cpu_worker_tile, [(x0, y, x1, y + 1, s0, s1) for y in range(y0, y1)], chunksize=1)
         return np.concatenate(rows, axis=0)
 
+    def tile_film(self, x0, y0, x1, y1, s0, s1):
+        """(sum[(px, N+1)], mean, m2) of the tile over ALL samples [s0, s1): pixels split over the pool, every pixel whole."""
+        import numpy as np
+        cols = max(1, (x1 - x0) // 4)
+        jobs = [(x, y, min(x + cols, x1), y + 1, s0, s1) for y in range(y0, y1) for x in range(x0, x1, cols)]
+        parts = self.pool.map(_cpu_worker_tile_film, jobs, chunksize=1)
+        return tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(3))
+
     def close(self):
         self.pool.close()
         self.pool.join()
@@ -173,7 +206,7 @@ def run_reference_arm(a):
     line = {
         "impl": "reference", "metric": "camera_paths_per_sec", "value": value, "unit": "paths/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": f"shipped scene assets/scenes/{a.scene}.scn",
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": f"shipped scene assets/scenes/{a.scene}.scn",
         "config": {"workload": workload_name(a), "note": "CPU arm renders a bounded sample of the same workload: cost per sample pass is independent of spp"},
         "cpu_baseline": {"value": value, "unit": "paths/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -240,7 +273,53 @@ def algorithmic_flops_per_path(scene, st, n):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 
+class SharedHostFilm:
+    """One page-locked host film that every rank of the node writes its own slice into (POSIX shared memory mapped and
+    cudaHostRegister-ed by every process): the host-side destination of the per-rank read-back.  Plumbing only."""
+
+    def __init__(self, torch, dist, npix, n, rank, world):
+        import mmap
+        import numpy as np
+        self.torch = torch
+        self.bytes = (3 * npix * n + npix) * 4
+        name = [f"/dev/shm/drt_film_{os.getpid()}" if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path, self.owner = name[0], rank == 0
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.bytes)
+        if world > 1:
+            dist.barrier()
+        self.fd = os.open(self.path, os.O_RDWR)
+        self.mm = mmap.mmap(self.fd, self.bytes)
+        flat = np.frombuffer(self.mm, dtype=np.float32)
+        self.ptr = flat.ctypes.data
+        rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.bytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        self.planes = {"sum": flat[:npix * n].reshape(npix, n), "mean": flat[npix * n:2 * npix * n].reshape(npix, n),
+                       "m2": flat[2 * npix * n:3 * npix * n].reshape(npix, n), "filter": flat[3 * npix * n:]}
+
+    def drt_film(self, cuda):
+        p = self.planes
+        return cuda.Film(p["sum"].ctypes.data, p["filter"].ctypes.data, p["mean"].ctypes.data, p["m2"].ctypes.data)
+
+    def close(self):
+        try:
+            self.torch.cuda.cudart().cudaHostUnregister(self.ptr)
+        except Exception:
+            pass
+        self.planes = None
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def run_b200_arm(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import common
@@ -259,62 +338,52 @@ def run_b200_arm(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    cfg, tables, scene, camera = common.load(a.scene, a.width, a.height, a.spp, a.depth)
+    spp_total, spp_rank = samples(a, world)
+    if a.scaling == "strong" and spp_total % world:
+        raise SystemExit(f"--spp {a.spp} is not a multiple of {world} ranks")
+    cfg, tables, scene, camera = common.load(a.scene, a.width, a.height, spp_rank, a.depth)
     n = scene.num_wavelengths
+    npix = a.width * a.height
     ctx = cuda.Context(local)
     ctx.upload_scene(scene, camera, tables)
     ctx.set_geometry_precision(cuda.GEOMETRY_F64 if a.geometry == "f64" else cuda.GEOMETRY_F32)
     dev = torch.device("cuda", local)
-    peers, merge_kind = None, "none"
-    if world > 1 and a.merge in ("scatter", "p2p"):
-        try:
-            peers = film_mod.PeerFilmGroup(ctx, a.width, a.height, scatter=a.merge == "scatter")
-            merge_kind = ("scatter: the render kernel stores each finished pixel into its owner's staging film over NVLink (CUDA IPC), "
-                          "then one local merge+images kernel per rank") if a.merge == "scatter" else \
-                         "p2p: one fused gather-merge+images kernel per rank over CUDA-IPC peer memory"
-        except Exception as exc:
-            print(f"[rank {rank}] peer-memory merge unavailable ({exc}); using NCCL", file=sys.stderr)
-            peers = None
-    if world > 1 and peers is None:
-        merge_kind = "nccl: 2 all_reduce + 1 reduce"
+    stream = torch.cuda.current_stream()
 
-    class _DevArray:   # view of library-owned device memory for torch copies (plumbing only)
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-    npix_all = a.width * a.height
-    if peers is not None:
-        drt_film = peers.mine
-        film = None
-        root_planes = None
-        if rank == 0:
-            m = peers.merged
-            root_planes = {"sum": torch.as_tensor(_DevArray(m.sum, (npix_all, n)), device=dev),
-                           "filter": torch.as_tensor(_DevArray(m.filter, (npix_all,)), device=dev),
-                           "mean": torch.as_tensor(_DevArray(m.mean, (npix_all, n)), device=dev),
-                           "m2": torch.as_tensor(_DevArray(m.m2, (npix_all, n)), device=dev)}
-    else:
+    group, film, merge_kind = None, None, "none (one GPU)"
+    if world > 1 and a.merge == "sharded":
+        group = film_mod.ShardedFilmGroup(ctx, a.width, a.height)
+        merge_kind = ("sharded: the render kernel stores each finished pixel into its owner's staging film over NVLink (CUDA IPC), device-side "
+                      "arrival flags instead of host barriers, one local merge+images kernel per rank, merged film stays sharded over the owners")
+    elif world > 1:
+        merge_kind = "nccl: 2 all_reduce + 1 reduce into rank 0"
+    if group is None:
         film = film_mod.FilmPlanes(a.width, a.height, n, dev)
         drt_film = film.as_drt_film()
-        root_planes = {"sum": film.sum, "filter": film.filter, "mean": film.mean, "m2": film.m2}
 
-    def combine():
-        if peers is not None:
-            return peers.merge(stream.cuda_stream, stream.synchronize)
-        return film_mod.merge_distributed_(film)
-    stream = torch.cuda.current_stream()
-    prm = common.structs.RenderParams(a.width, a.height, rank * a.spp, (rank + 1) * a.spp, a.depth, cfg.pixel_scheme, a.seed)
-    paths_per_step = a.width * a.height * a.spp * world
+    def params_for(per_rank):
+        return common.structs.RenderParams(a.width, a.height, rank * per_rank, (rank + 1) * per_rank, a.depth, cfg.pixel_scheme, a.seed)
 
-    def render():
-        if peers is not None:
-            peers.render(prm, stream.cuda_stream)
-        else:
-            ctx.render_device(prm, drt_film, accumulate=False, stream=stream.cuda_stream)
+    prm = params_for(spp_rank)
+    paths_per_step = npix * spp_total
+    marks = None
 
-    def step():
-        render()
-        return combine()
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            marks[-1][name] = ev
+
+    def step(p=None):
+        """One complete render of the workload on this rank's stream; returns the number of kernels launched."""
+        p = p or prm
+        if group is not None:
+            return group.step(p, stream.cuda_stream, mark if marks is not None else None)
+        ctx.render_device(p, drt_film, accumulate=False, stream=stream.cuda_stream)
+        mark("render")
+        if world > 1:
+            film_mod.merge_distributed_(film)       # NCCL collectives + torch elementwise kernels: library work, not counted
+        return 1
 
     def fence():
         torch.cuda.synchronize()
@@ -322,58 +391,87 @@ def run_b200_arm(a):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(p, steps):
+        """(ms per step: max over ranks of the CUDA-event time of `steps` steps, launches per step, per-step phase events)"""
+        nonlocal marks
+        fence()
+        marks = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        e0.record(stream)
+        for _ in range(steps):
+            marks.append({})
+            mark("start")
+            launches += step(p)
+        e1.record(stream)
+        fence()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        got, marks = marks, None
+        return float(ms.item()) / steps, launches // steps, got
+
     peak_tf = ctx.measure_fp32_peak(False) if rank == 0 else 0.0
     for _ in range(max(a.warmup, 3)):
         step()
     fence()
     sampler = ClockSampler(local) if rank == 0 else None
-    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
     t0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(a.steps):
-        k_start[i].record(stream)
-        render()
-        k_stop[i].record(stream)
-        combine()
-        launches += 1 + (1 if peers is not None else 0)
-    e1.record(stream)
-    fence()
+    ms_step, launches_step, ev = timed(prm, a.steps)
     t1 = time.perf_counter()
-    merge_ms = None
-    if peers is not None:      # one more (untimed) step with the exchange's phases timed on the host
-        peers.timing = []
-        step()
-        fence()
-        merge_ms = {k: 1e3 * v for k, v in zip(("wait_own_render", "barrier_before", "merge_kernel", "barrier_after"), peers.timing[-1])}
-        peers.timing = None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
-    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(k_start, k_stop)) / a.steps
     clocks = sampler.stop(t0, t1) if sampler else None
+    kernel_ms = sum(m["start"].elapsed_time(m["render"]) for m in ev) / len(ev)
+    exchange_ms = None
+    if group is not None:
+        group.check()
+        phases = {"render_kernel": ("start", "render"), "signal_and_wait_for_all_ranks": ("render", "arrived"),
+                  "merge_kernel": ("arrived", "merged"), "completion_flags": ("merged", "done")}
+        mine = torch.tensor([sum(m[x].elapsed_time(m[y]) for m in ev) / len(ev) for x, y in phases.values()], device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        exchange_ms = {k: {"rank0": float(allr[0][i]), "max_over_ranks": float(max(t[i] for t in allr))} for i, k in enumerate(phases)}
     st = ctx.stats()
 
-    # ---- end to end through host buffers: scene upload (H2D) + render (+ NCCL merge) + film read-back (D2H), every step
-    npix = a.width * a.height
-    pinned = {k: torch.empty(shape, dtype=torch.float32).pin_memory()
-              for k, shape in (("sum", (npix, n)), ("filter", (npix,)), ("mean", (npix, n)), ("m2", (npix, n)))} if rank == 0 else None
-    host_film = cuda.Film(*(pinned[k].data_ptr() for k in ("sum", "filter", "mean", "m2"))) if rank == 0 else None
+    # ---- the other scaling mode as an extra figure (N > 1): weak = every GPU renders `spp` samples, strong = `spp` in total
+    other = None
+    if world > 1:
+        per = a.spp if a.scaling == "strong" else a.spp // world
+        if per >= 1:
+            p2 = params_for(per)
+            step(p2)
+            ms2, _, _ = timed(p2, a.steps)
+            other = {"scaling": "weak" if a.scaling == "strong" else "strong", "samples_per_pixel_total": per * world,
+                     "value": npix * per * world / (ms2 * 1e-3), "unit": "paths/s", "ms_per_step": ms2}
+
+    # ---- end to end through host buffers, every step: scene upload (H2D) + render + exchange + film read-back (D2H).
+    # N = 1: the C-ABI host-buffer call drt_cuda_render_host.  N > 1 (sharded): every rank reads ITS merged slice back into one
+    # shared page-locked host film over its own PCIe link (drt_cuda_film_read_slice); nccl: rank 0 reads the whole film back.
+    host = SharedHostFilm(torch, dist, npix, n, rank, world) if (world == 1 or group is not None) else None
+    pinned = None
+    if host is None and rank == 0:
+        pinned = {k: torch.empty(shape, dtype=torch.float32).pin_memory()
+                  for k, shape in (("sum", (npix, n)), ("filter", (npix,)), ("mean", (npix, n)), ("m2", (npix, n)))}
+    host_film = host.drt_film(cuda) if host is not None else None
+    d2h = [0]
 
     def e2e_step():
         ctx.upload_scene(scene, camera, tables)
         if world == 1:
-            ctx.render_host_into(prm, host_film)           # the C-ABI host-buffer call of include/drt_cuda.h
+            ctx.render_host_into(prm, host_film)
+            d2h[0] = (3 * npix * n + npix) * 4
+        elif group is not None:
+            step()
+            d2h[0] = group.read_back(host_film, stream.cuda_stream)
+            stream.synchronize()
         else:
-            render()
-            combine()
+            step()
             if rank == 0:
-                for k in ("sum", "filter", "mean", "m2"):
-                    pinned[k].copy_(root_planes[k], non_blocking=True)
+                for k, t in (("sum", film.sum), ("filter", film.filter), ("mean", film.mean), ("m2", film.m2)):
+                    pinned[k].copy_(t, non_blocking=True)
+                d2h[0] = (3 * npix * n + npix) * 4
             torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()          # the step is over when the whole film is in host memory
 
     e2e_step()
     fence()
@@ -382,24 +480,34 @@ def run_b200_arm(a):
         e2e_step()
     fence()
     e2e_s = torch.tensor([time.perf_counter() - te0], device="cuda")
+    d2h_all = torch.tensor([float(d2h[0])], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d2h_all, op=dist.ReduceOp.SUM)
     e2e_s = float(e2e_s.item())
-    upload_bytes = ctx.scene_upload_bytes()
-    d2h_bytes = (3 * npix * n + npix) * 4
+    upload_bytes = ctx.scene_upload_bytes() * world
+    d2h_bytes = int(d2h_all.item())
+    if group is not None:
+        group.check()
 
     if rank == 0:
         kinfo = ctx.render_kernel_info(prm)
         flops_path, rc, rs, b = algorithmic_flops_per_path(scene, st, n)
-        paths_launch = a.width * a.height * a.spp
+        paths_launch = npix * spp_rank
         achieved_tf = flops_path * paths_launch / (kernel_ms * 1e-3) / 1e12
+        # pixels outside the scene's screen-space bound are counted, not traced (exact; drt_cuda_analyse_scene): the fraction of
+        # camera paths the kernel executes, and the roofline fraction on executed work alone
+        hx0, hy0, hx1, hy1 = cuda.analyse_scene(scene, camera, a.width, a.height)[0]
+        traced_fraction = (hx1 - hx0) * (hy1 - hy0) / npix
+        per_ray = sum(33 if scene.surfaces[i].type == 3 else 24 if scene.surfaces[i].type == 2 else 0 for i in range(scene.num_surfaces))
+        culled_flops = (1.0 - traced_fraction) * ((per_ray + 32) + 8 * n + 40)       # one closest-hit ray, film update, camera
+        executed_tf = (flops_path - culled_flops) * paths_launch / (kernel_ms * 1e-3) / 1e12
         film_bytes = (3 * npix * n + npix) * 4
-        hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
-        value = paths_per_step * a.steps / (ms_total * 1e-3)
+        value = paths_per_step / (ms_step * 1e-3)
         traffic = None
         try:
             tj = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
@@ -409,22 +517,29 @@ def run_b200_arm(a):
             traffic = None
         line = {
             "metric": "camera_paths_per_sec", "value": value, "unit": "paths/s", "n_gpus": world, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f32", "impl": "b200",
             "data": f"shipped scene assets/scenes/{a.scene}.scn through the legacy-compat parser; per-path Philox4x32-10 streams, seed {a.seed}",
             "config": {"workload": workload_name(a), "geometry": a.geometry, "film_merge": merge_kind,
-                       "l2": "inputs (scene + spectra, < 64 KB) live in shared memory; each step writes 4 fresh film planes "
-                             f"({film_bytes / 1e6:.0f} MB > 126 MB L2), nothing is re-read between steps",
-                       "samples_per_pixel_total": a.spp * world},
+                       "l2": "inputs (scene + spectra, < 64 KB) live in shared memory; each step writes fresh film planes "
+                             f"({film_bytes / 1e6:.0f} MB in all > 126 MB L2), nothing is re-read between steps",
+                       "samples_per_pixel_total": spp_total, "samples_per_pixel_per_gpu": spp_rank},
             "rays_per_sec": value * (rc + rs),
             "rays_per_path": {"closest": rc, "shadow": rs, "shaded_bounces": b},
+            "paths_traced_fraction": traced_fraction,
             "clocks": clocks,
             "e2e": {"value": paths_per_step * a.steps / e2e_s, "unit": "paths/s", "h2d_bytes_per_step": upload_bytes,
-                    "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches,
-            "film_exchange_ms": merge_ms,
+                    "d2h_bytes_per_step": d2h_bytes,
+                    "note": "scene upload + render (+ exchange) + film read-back into page-locked host memory, wall clock, max over ranks"
+                            + ("; every rank reads its own merged slice back over its own PCIe link into one shared host film" if group is not None else "")},
+            "gpu_launches": launches_step * a.steps,
+            "film_exchange_ms": exchange_ms,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "frac": achieved_tf / peak_tf if peak_tf else None,
+                         "frac_executed": executed_tf / peak_tf if peak_tf else None,
+                         "frac_note": "frac bills every camera path at the reference's arithmetic (SURVEY.md 8d), frac_executed leaves out the "
+                                      "paths of pixels that provably see nothing and are counted instead of traced (paths_traced_fraction)",
+                         "traffic": traffic,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (profiles/ncu_traffic.json); null for other image sizes",
                          "kernel": kinfo[0], "warps_per_cta": kinfo[1], "ctas_per_sm": kinfo[2], "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_path": flops_path,
@@ -433,47 +548,73 @@ def run_b200_arm(a):
                                  "frac": film_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": "algorithmic HBM bytes per launch = one write of the four film planes"}},
         }
-        if world == 1 and not a.no_cpu_baseline:
+        if other is not None:
+            line[other["scaling"]] = other
+        if not a.no_cpu_baseline:
             try:
                 arm = CpuArm(a)
-                arm.step(0, rows=max(64, a.height // 8))
-                paths, secs = 0, 0.0
-                passes = 0
-                while secs < 10.0 and passes < 256:   # a bounded sample: about 10 s of work on all host cores
-                    p, t = arm.step(1 + passes)
-                    paths += p
-                    secs += t
-                    passes += 1
-                # image RMSE against the reference on the same per-path random streams: a central tile, 8 samples per pixel
+                # image RMSE against the reference on the SAME per-path random streams, every N: a tile of the film the e2e leg left
+                # in host memory (for N > 1 it straddles two owners' slices) against the reference's film of all GLOBAL sample indices
                 try:
-                    import numpy as np
-                    tw = min(64, a.width); th = min(64, a.height)
-                    x0, y0 = (a.width - tw) // 2, (a.height - th) // 2
-                    prm8 = common.structs.RenderParams(a.width, a.height, 0, 8, a.depth, cfg.pixel_scheme, a.seed)
-                    ref_paths = arm.tile_paths(x0, y0, x0 + tw, y0 + th, 0, 8)
-                    gpu_paths = ctx.sample_paths(prm8, x0, y0, x0 + tw, y0 + th)
-                    ref_mean, gpu_mean = ref_paths.mean(axis=1), gpu_paths.astype(np.float64).mean(axis=1)
-                    rmse = float(np.sqrt(np.mean((gpu_mean - ref_mean) ** 2)))
-                    perr = common.path_errors(gpu_paths, ref_paths)
-                    line["image_rmse"] = {"value": rmse, "relative": rmse / float(np.abs(ref_mean).mean()),
-                                          "unit": "spectral radiance, RMSE over pixels and wavelengths of the 8-sample mean",
-                                          "tile": f"{tw}x{th} at the image centre, samples 0-7, {ref_paths.shape[0] * 8} paths",
-                                          "rng": "matched: both sides draw the same per-path Philox streams",
-                                          "paths_within_1e-3": float((perr <= 1e-3).mean()), "reference": arm.kind}
+                    line["image_rmse"] = image_check(a, arm, ctx, common, cfg, host.planes if host is not None else {k: v.numpy() for k, v in pinned.items()},
+                                                     n, spp_total, world)
                 except Exception as exc:
                     line["image_rmse"] = {"value": None, "error": repr(exc)}
+                if world == 1:
+                    arm.step(0, rows=max(64, a.height // 8))
+                    paths, secs, passes = 0, 0.0, 0
+                    while secs < 10.0 and passes < 256:   # a bounded sample: about 10 s of work on all host cores
+                        p, t = arm.step(1 + passes)
+                        paths += p
+                        secs += t
+                        passes += 1
+                    line["cpu_baseline"] = {"value": paths / secs, "unit": "paths/s", "cores": arm.cores, "kind": arm.kind,
+                                            "sample": f"{passes} full-frame passes of {a.width}x{a.height} at 1 sample per pixel ({paths} paths, {secs:.1f} s), "
+                                                      f"one single-threaded process per core"}
                 arm.close()
-                line["cpu_baseline"] = {"value": paths / secs, "unit": "paths/s", "cores": arm.cores, "kind": arm.kind,
-                                        "sample": f"{passes} full-frame passes of {a.width}x{a.height} at 1 sample per pixel ({paths} paths, {secs:.1f} s), "
-                                                  f"one single-threaded process per core"}
             except Exception as exc:   # the baseline is reported, never a gate
                 line["cpu_baseline"] = {"value": None, "unit": "paths/s", "cores": _cpu_cores(), "kind": "unavailable", "sample": repr(exc)}
         print(json.dumps(line), flush=True)
-    if peers is not None:
-        peers.close()
+    if world > 1:
+        dist.barrier()
+    if host is not None:
+        host.close()
+    if group is not None:
+        group.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def image_check(a, arm, ctx, common, cfg, planes, n, spp_total, world):
+    """Film of a centre tile, GPU (as read back by the e2e leg) against the reference over the same global sample indices."""
+    import numpy as np
+    tw, th = min(32, a.width), min(32, a.height)
+    # keep the CPU side bounded (about 4 M paths): a thinner tile for very large sample counts
+    while tw * th * spp_total > (1 << 22) and th > 2:
+        th //= 2
+    x0, y0 = (a.width - tw) // 2, (a.height - th) // 2
+    r_sum, r_mean, r_m2 = arm.tile_film(x0, y0, x0 + tw, y0 + th, 0, spp_total)
+    idx = np.array([(y0 + j) * a.width + x0 + i for j in range(th) for i in range(tw)])
+    g_sum, g_mean, g_m2, g_cnt = (planes[k][idx].astype(np.float64) for k in ("sum", "mean", "m2", "filter"))
+    rmse = float(np.sqrt(np.mean((g_mean - r_mean) ** 2)))
+    rel = rmse / float(np.abs(r_mean).mean())
+
+    def worst(g, r):
+        return float((np.abs(g - r) / np.maximum(np.abs(r), 1e-4 * np.abs(r).max())).max())
+    out = {"value": rmse, "relative": rel, "unit": "spectral radiance, RMSE over pixels and wavelengths of the film mean",
+           "tile": f"{tw}x{th} at the image centre, all {spp_total} global samples per pixel ({tw * th * spp_total} paths), film as read back by the e2e leg",
+           "rng": "matched: both sides draw the same per-path Philox streams (keyed by pixel and GLOBAL sample index)",
+           "sample_count_exact": bool((g_cnt == spp_total).all()),
+           "max_rel_err": {"sum": worst(g_sum, r_sum[:, :n]), "mean": worst(g_mean, r_mean), "m2": worst(g_m2, r_m2)},
+           "reference": arm.kind, "n_gpus": world,
+           "ok": bool(rel <= 1e-3 and (g_cnt == spp_total).all())}
+    if world == 1:
+        prm8 = common.structs.RenderParams(a.width, a.height, 0, 8, a.depth, cfg.pixel_scheme, a.seed)
+        ref_paths = arm.tile_paths(x0, y0, x0 + tw, y0 + th, 0, 8)
+        gpu_paths = ctx.sample_paths(prm8, x0, y0, x0 + tw, y0 + th)
+        out["paths_within_1e-3"] = float((common.path_errors(gpu_paths, ref_paths) <= 1e-3).mean())
+    return out
 
 
 def main():

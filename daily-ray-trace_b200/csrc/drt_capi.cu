@@ -12,24 +12,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "drt_cuda.h"
-#include "drt_device.cuh"
-
-cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-int         drt_render_cta_warps(bool f64_geometry, bool all_fast);
-size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots);
-void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
-                                   float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
-void        drt_launch_film_merge(FilmPtrs dst, FilmPtrs src, uint32_t n, size_t npix, int grid, cudaStream_t stream);
-void        drt_launch_fma_peak(int packed, float *out, int iters, int grid, cudaStream_t stream);
-void        drt_launch_film_gather_merge(const void *tables, int count, const FilmPtrs *films, FilmPtrs dst, uint32_t pixel_begin, uint32_t pixel_end, uint32_t src_base, uint32_t dst_base,
-                                         uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, int grid, cudaStream_t stream);
-size_t      drt_rgb_tables_bytes(void);
-void        drt_fill_rgb_tables(void *dst_host, const drt_tables *t);
+#include "drt_context.cuh"
 
 static thread_local char g_err[512];
 
-static int fail(int code, const char *fmt, ...)
+int drt_fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -37,48 +24,6 @@ static int fail(int code, const char *fmt, ...)
     va_end(ap);
     return code;
 }
-
-#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while(0)
-
-#define DRT_RING 64
-
-struct drt_cuda_context
-{
-    int    device = 0;
-    int    num_sms = 0;
-    size_t smem_optin = 0;
-    bool   have_scene = false;
-    bool   f64_geometry = false;
-    int    n = 0, nslots = 0, nlights = 0, eval_words = 1;
-    bool   hit_bound = false;      /* hit_u/v: film-plane bound (in pixel units of the uploaded camera) of everything a camera ray can hit */
-    double hit_u0 = 0, hit_u1 = 0, hit_v0 = 0, hit_v1 = 0;
-    bool   all_fast = false;      /* every surface material has a plastic block (SpdIndex::plastic): the specialised kernel applies */
-    void  *d_geom32 = nullptr, *d_geom64 = nullptr;
-    SpdIndex *d_index = nullptr;
-    float *d_pool = nullptr;
-    uint32_t pool_words = 0;
-    size_t pool_capacity = 0;
-    void  *d_rgb_tables = nullptr;
-    /* Work counters and the task counter are PER CALL, taken round-robin from two small rings, so that renders of one context that
-     * are in flight on different streams (a user stream, render_host's band streams, the legacy stream of sample_paths) never
-     * share a counter: stats_ring[i] belongs to the i-th most recent render call (the bands of one render_host call share one),
-     * counter_ring[i] to one kernel launch.  A slot is reused after DRT_RING calls; get_stats reads the latest call's block.
-     * (The library's growing buffers d_film / d_dump / d_slice are reallocated with cudaFree, which waits for the device.) */
-    DeviceStats *d_stats_ring = nullptr;
-    unsigned int *d_counter_ring = nullptr;
-    uint64_t stats_calls = 0, counter_launches = 0;
-    DeviceStats *d_stats = nullptr;       /* the current call's block inside d_stats_ring */
-    /* library-owned film + dump buffers for the host-buffer entry points */
-    float *d_film = nullptr; size_t film_bytes = 0;
-    float *d_dump = nullptr; size_t dump_bytes = 0;
-    float *d_slice = nullptr; size_t slice_bytes = 0;   /* merged planes of this rank's slice before they are copied to the root */
-    uint64_t launches = 0;
-    size_t upload_bytes = 0;
-    uint64_t last_launches = 0;
-    /* render_host pipelines the frame in row bands: render on one stream, read finished bands back on the other */
-    cudaStream_t band_render = nullptr, band_copy = nullptr;
-    cudaEvent_t  band_done[16] = {};
-};
 
 extern "C" const char *drt_cuda_last_error(void) { return g_err; }
 
@@ -122,6 +67,7 @@ extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
     cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats_ring); cudaFree(ctx->d_counter_ring); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice);
+    drt_exchange_release(ctx);
     if(ctx->band_render) cudaStreamDestroy(ctx->band_render);
     if(ctx->band_copy) cudaStreamDestroy(ctx->band_copy);
     for(int i = 0; i < 16; i += 1) if(ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
@@ -575,7 +521,7 @@ static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int
 
 extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_render_params *params, char *name, size_t name_len, int *warps_per_cta, int *ctas_per_sm)
 {
-    if(!ctx || !params || params->max_depth == 0 || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "bad argument");
+    if(!ctx || !params || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "bad argument");
     const uint32_t max_depth = params->max_depth;
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     RenderLaunch L;
@@ -599,9 +545,28 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
 {
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
-    if(p->sample_end <= p->sample_begin) return fail(DRT_CUDA_E_ARG, "empty sample range [%u,%u)", p->sample_begin, p->sample_end);
-    if(p->max_depth == 0) return fail(DRT_CUDA_E_ARG, "max_depth 0");
+    if(p->sample_end < p->sample_begin) return fail(DRT_CUDA_E_ARG, "bad sample range [%u,%u)", p->sample_begin, p->sample_end);
     CU(cudaSetDevice(ctx->device));
+    if(p->sample_end == p->sample_begin)
+    {
+        /* num_pixel_samples 0: render_image's sample loop does not run (daily_ray_trace.c:710) and the films stay as allocated, all zero */
+        if(path_words_out) *path_words_out = 0;
+        if(!keep_stats)
+        {
+            ctx->d_stats = ctx->d_stats_ring + (ctx->stats_calls++ % DRT_RING);
+            CU(cudaMemsetAsync(ctx->d_stats, 0, sizeof(DeviceStats), stream));
+        }
+        ctx->last_launches = 0;
+        if(film.sum && !accumulate && scatter_count == 0)
+        {
+            const size_t n = (size_t)ctx->n, w = p->width;
+            if(x0 != 0 || x1 != p->width) return fail(DRT_CUDA_E_ARG, "empty sample range on a partial-width rectangle");
+            const size_t at = (size_t)y0 * w, cnt = (size_t)(y1 - y0) * w;
+            CU(cudaMemsetAsync(film.sum + at * n, 0, cnt * n * 4, stream)); CU(cudaMemsetAsync(film.mean + at * n, 0, cnt * n * 4, stream));
+            CU(cudaMemsetAsync(film.m2 + at * n, 0, cnt * n * 4, stream));  CU(cudaMemsetAsync(film.filter + at, 0, cnt * 4, stream));
+        }
+        return DRT_CUDA_OK;
+    }
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.geom = ctx->f64_geometry ? ctx->d_geom64 : ctx->d_geom32;
@@ -615,7 +580,8 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     for(int i = 0; i < scatter_count; i += 1) L.scatter[i] = FilmPtrs{ scatter[i].sum, scatter[i].filter, scatter[i].mean, scatter[i].m2 };
     L.scatter_count = (uint32_t)scatter_count; L.scatter_rank = (uint32_t)scatter_rank; L.scatter_slice = (uint32_t)scatter_slice;
     uint32_t rect[4];
-    hit_rect(ctx->hit_bound, ctx->hit_u0, ctx->hit_u1, ctx->hit_v0, ctx->hit_v1, p->width, p->height, rect);
+    /* max_cast_depth 0 casts no ray at all (cast_ray's loop, daily_ray_trace.c:446): nothing to cull, and the culled pixels' "one closest-hit ray" must not be counted */
+    hit_rect(ctx->hit_bound && p->max_depth > 0, ctx->hit_u0, ctx->hit_u1, ctx->hit_v0, ctx->hit_v1, p->width, p->height, rect);
     L.hit_x0 = rect[0]; L.hit_y0 = rect[1]; L.hit_x1 = rect[2]; L.hit_y1 = rect[3];
     record_layout(ctx, p->max_depth, L);
     if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
@@ -664,7 +630,7 @@ extern "C" int drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_r
     return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, (cudaStream_t)stream, nullptr, nullptr, staging, count, rank, slice_pixels);
 }
 
-static int ensure(float **buf, size_t *have, size_t need)
+int drt_ensure_buffer(float **buf, size_t *have, size_t need)
 {
     if(*have >= need) return DRT_CUDA_OK;
     cudaFree(*buf); *buf = nullptr; *have = 0;
@@ -679,7 +645,7 @@ extern "C" int drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_para
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     CU(cudaSetDevice(ctx->device));
     size_t npix = (size_t)params->width * params->height, plane = npix * (size_t)ctx->n * 4, fplane = npix * 4;
-    int rc = ensure(&ctx->d_film, &ctx->film_bytes, 3 * plane + fplane);
+    int rc = drt_ensure_buffer(&ctx->d_film, &ctx->film_bytes, 3 * plane + fplane);
     if(rc != DRT_CUDA_OK) return rc;
     float *base = ctx->d_film;
     FilmPtrs f = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
@@ -742,7 +708,7 @@ extern "C" int drt_cuda_sample_paths(drt_cuda_context *ctx, const drt_render_par
     if(x1 <= x0 || y1 <= y0 || params->sample_end <= params->sample_begin) return fail(DRT_CUDA_E_ARG, "empty rectangle or sample range");
     CU(cudaSetDevice(ctx->device));
     size_t bytes = (size_t)(x1 - x0) * (y1 - y0) * (params->sample_end - params->sample_begin) * (size_t)ctx->n * 4;
-    int rc = ensure(&ctx->d_dump, &ctx->dump_bytes, bytes);
+    int rc = drt_ensure_buffer(&ctx->d_dump, &ctx->dump_bytes, bytes);
     if(rc != DRT_CUDA_OK) return rc;
     FilmPtrs none = { nullptr, nullptr, nullptr, nullptr };
     rc = launch(ctx, params, x0, y0, x1, y1, none, ctx->d_dump, 0, 0);
@@ -763,7 +729,7 @@ extern "C" int drt_cuda_debug_records(drt_cuda_context *ctx, const drt_render_pa
     if(rc != DRT_CUDA_OK || !out_host) return rc;
     size_t words = (size_t)(x1 - x0) * (y1 - y0) * (params->sample_end - params->sample_begin) * (size_t)*words_per_path;
     if(words > out_capacity_words) return fail(DRT_CUDA_E_ARG, "record buffer too small: need %zu words", words);
-    rc = ensure(&ctx->d_dump, &ctx->dump_bytes, words * 4);
+    rc = drt_ensure_buffer(&ctx->d_dump, &ctx->dump_bytes, words * 4);
     if(rc != DRT_CUDA_OK) return rc;
     rc = launch(ctx, params, x0, y0, x1, y1, none, nullptr, 0, 0, ctx->d_dump, nullptr);
     if(rc != DRT_CUDA_OK) return rc;
@@ -962,7 +928,7 @@ extern "C" int drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film 
          * memory) as four contiguous copies: the copy engines move large blocks over NVLink about twice as fast as the
          * kernel's 4-byte-per-lane peer stores did (measured: 763 MB into the root in 2.2 ms from kernel stores) */
         const size_t spx = (size_t)(pixel_end - pixel_begin), plane = spx * n * 4;
-        int rc = ensure(&ctx->d_slice, &ctx->slice_bytes, 3 * plane + spx * 4);
+        int rc = drt_ensure_buffer(&ctx->d_slice, &ctx->slice_bytes, 3 * plane + spx * 4);
         if(rc != DRT_CUDA_OK) return rc;
         float *base = ctx->d_slice;
         FilmPtrs d = { base, base + 3 * (plane / 4), base + plane / 4, base + 2 * (plane / 4) };
@@ -977,76 +943,6 @@ extern "C" int drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film 
         ctx->launches += 1;
     }
     return DRT_CUDA_OK;
-}
-
-/* One process, several devices: the scattered exchange of bench.py without IPC (all pointers live in one address space). */
-extern "C" int drt_cuda_render_host_multi(drt_cuda_context **ctxs, int count, const drt_render_params *params, const drt_film *out)
-{
-    if(!ctxs || count < 1 || count > DRT_MAX_PEERS || !params || !out || !out->sum || !out->filter || !out->mean || !out->m2)
-        return fail(DRT_CUDA_E_ARG, "bad argument (1..%d contexts)", DRT_MAX_PEERS);
-    for(int g = 0; g < count; g += 1)
-    {
-        if(!ctxs[g] || !ctxs[g]->have_scene) return fail(DRT_CUDA_E_STATE, "context %d has no scene", g);
-        if(ctxs[g]->n != ctxs[0]->n) return fail(DRT_CUDA_E_ARG, "context %d holds another scene", g);
-        for(int h = 0; h < g; h += 1) if(ctxs[h]->device == ctxs[g]->device) return fail(DRT_CUDA_E_ARG, "contexts %d and %d share device %d", h, g, ctxs[g]->device);
-    }
-    if(count == 1) return drt_cuda_render_host(ctxs[0], params, out);
-    const uint32_t spp = params->sample_end > params->sample_begin ? params->sample_end - params->sample_begin : 0;
-    if(spp < (uint32_t)count) return fail(DRT_CUDA_E_ARG, "%u samples per pixel cannot be split over %d devices", spp, count);
-    const size_t n = (size_t)ctxs[0]->n, npix = (size_t)params->width * params->height;
-    const uint64_t slice = (npix + (size_t)count - 1) / (size_t)count;
-    const uint32_t rows = (uint32_t)((slice * (uint64_t)count + params->width - 1) / params->width);
-
-    drt_film staging[DRT_MAX_PEERS];
-    memset(staging, 0, sizeof(staging));
-    drt_film merged;
-    memset(&merged, 0, sizeof(merged));
-    int rc = DRT_CUDA_OK;
-    /* peer access both ways, a staging film per device, the merged film on device 0 */
-    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
-    {
-        if(cudaSetDevice(ctxs[g]->device) != cudaSuccess) { rc = fail(DRT_CUDA_E_CUDA, "cudaSetDevice(%d)", ctxs[g]->device); break; }
-        for(int h = 0; h < count; h += 1)
-        {
-            if(h == g) continue;
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, ctxs[g]->device, ctxs[h]->device);
-            if(!can) { rc = fail(DRT_CUDA_E_UNSUPPORTED, "device %d cannot access device %d", ctxs[g]->device, ctxs[h]->device); break; }
-            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[h]->device, 0);
-            if(e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            else if(e != cudaSuccess) { rc = fail(DRT_CUDA_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); break; }
-        }
-        if(rc == DRT_CUDA_OK) rc = drt_cuda_film_alloc(ctxs[g], params->width, rows, &staging[g]);
-    }
-    if(rc == DRT_CUDA_OK) rc = drt_cuda_film_alloc(ctxs[0], params->width, params->height, &merged);
-    /* every device renders its share of the samples of every pixel and stores finished pixels with their owner */
-    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
-    {
-        drt_render_params p = *params;
-        p.sample_begin = params->sample_begin + (uint32_t)((uint64_t)spp * g / count);
-        p.sample_end = params->sample_begin + (uint32_t)((uint64_t)spp * (g + 1) / count);
-        rc = drt_cuda_render_device_scatter(ctxs[g], &p, staging, count, g, slice, nullptr);
-    }
-    for(int g = 0; g < count; g += 1) { cudaSetDevice(ctxs[g]->device); if(cudaDeviceSynchronize() != cudaSuccess && rc == DRT_CUDA_OK) rc = fail(DRT_CUDA_E_CUDA, "render on device %d failed", ctxs[g]->device); }
-    /* every device merges its slice from local memory into the film on device 0 */
-    for(int g = 0; g < count && rc == DRT_CUDA_OK; g += 1)
-    {
-        const uint64_t p0 = (uint64_t)g * slice < npix ? (uint64_t)g * slice : npix, p1 = (uint64_t)(g + 1) * slice < npix ? (uint64_t)(g + 1) * slice : npix;
-        rc = drt_cuda_film_merge_slices(ctxs[g], &merged, &staging[g], count, slice, params->width, params->height, p0, p1, nullptr, nullptr, nullptr, nullptr);
-    }
-    for(int g = 0; g < count; g += 1) { cudaSetDevice(ctxs[g]->device); if(cudaDeviceSynchronize() != cudaSuccess && rc == DRT_CUDA_OK) rc = fail(DRT_CUDA_E_CUDA, "merge on device %d failed", ctxs[g]->device); }
-    if(rc == DRT_CUDA_OK)
-    {
-        cudaSetDevice(ctxs[0]->device);
-        cudaError_t e = cudaMemcpy(out->sum, merged.sum, npix * n * 4, cudaMemcpyDeviceToHost);
-        if(e == cudaSuccess) e = cudaMemcpy(out->mean, merged.mean, npix * n * 4, cudaMemcpyDeviceToHost);
-        if(e == cudaSuccess) e = cudaMemcpy(out->m2, merged.m2, npix * n * 4, cudaMemcpyDeviceToHost);
-        if(e == cudaSuccess) e = cudaMemcpy(out->filter, merged.filter, npix * 4, cudaMemcpyDeviceToHost);
-        if(e != cudaSuccess) rc = fail(DRT_CUDA_E_CUDA, "film read-back: %s", cudaGetErrorString(e));
-    }
-    for(int g = 0; g < count; g += 1) if(staging[g].sum) drt_cuda_film_free(ctxs[g], &staging[g]);
-    if(merged.sum) drt_cuda_film_free(ctxs[0], &merged);
-    return rc;
 }
 
 extern "C" int drt_cuda_measure_fp32_peak(drt_cuda_context *ctx, int packed, double *tflops)

@@ -17,7 +17,9 @@ EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "d
            "drt_cuda_get_stats", "drt_cuda_analyse_scene", "drt_cuda_validate_scene", "drt_cuda_render_kernel_info", "drt_cuda_sample_paths", "drt_cuda_film_to_rgb", "drt_cuda_film_merge",
            "drt_cuda_measure_fp32_peak", "drt_cuda_film_alloc", "drt_cuda_film_free", "drt_cuda_film_ipc_export",
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
-           "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close"]
+           "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close",
+           "drt_cuda_film_merge_slices_local", "drt_cuda_film_read_slice", "drt_cuda_flags_signal", "drt_cuda_flags_wait", "drt_cuda_flags_timeouts",
+           "drt_cuda_host_alloc", "drt_cuda_host_free"]
 
 
 class Film(C.Structure):
@@ -69,6 +71,14 @@ def lib():
         L.drt_cuda_film_merge_slices.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                                                  C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.drt_cuda_render_host.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film)]
+        L.drt_cuda_film_merge_slices_local.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                       C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.drt_cuda_film_read_slice.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint64, C.c_uint64, C.POINTER(Film), C.c_void_p]
+        L.drt_cuda_flags_signal.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_void_p]
+        L.drt_cuda_flags_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+        L.drt_cuda_flags_timeouts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.drt_cuda_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.drt_cuda_host_free.argtypes = [C.c_void_p]
         L.drt_cuda_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.drt_cuda_sample_paths.argtypes = [C.c_void_p, C.POINTER(RenderParams)] + [C.c_uint32] * 4 + [C.c_void_p]
         L.drt_cuda_film_to_rgb.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint32, C.c_uint32, C.c_int, C.c_void_p,
@@ -239,6 +249,26 @@ class Context:
         b = bgra or (None, None, None)
         _check(lib().drt_cuda_film_merge_slices(self._h, C.byref(dst), C.byref(staging), count, slice_pixels, width, height,
                                                 pixel_begin, pixel_end, b[0], b[1], b[2], stream))
+
+    def film_merge_slices_local(self, slice_film, staging, count, slice_pixels, width, height, pixel_begin, pixel_end, bgra=None, stream=None):
+        b = bgra or (None, None, None)
+        _check(lib().drt_cuda_film_merge_slices_local(self._h, C.byref(slice_film), C.byref(staging), count, slice_pixels, width, height,
+                                                      pixel_begin, pixel_end, b[0], b[1], b[2], stream))
+
+    def film_read_slice(self, slice_film, pixel_begin, pixel_end, host_film, stream=None):
+        _check(lib().drt_cuda_film_read_slice(self._h, C.byref(slice_film), pixel_begin, pixel_end, C.byref(host_film), stream))
+
+    def flags_signal(self, targets, value, stream=None):
+        arr = (C.c_void_p * len(targets))(*targets)
+        _check(lib().drt_cuda_flags_signal(self._h, arr, len(targets), value & 0xffffffff, stream))
+
+    def flags_wait(self, flags_ptr, count, value, stream=None):
+        _check(lib().drt_cuda_flags_wait(self._h, flags_ptr, count, value & 0xffffffff, stream))
+
+    def flags_timeouts(self):
+        v = C.c_uint32()
+        _check(lib().drt_cuda_flags_timeouts(self._h, C.byref(v)))
+        return v.value
 
     def measure_fp32_peak(self, packed=False):
         v = C.c_double()

@@ -70,94 +70,106 @@ def slice_partition(npix, world):
     return per, [(min(npix, r * per), min(npix, (r + 1) * per)) for r in range(world)]
 
 
-class PeerFilmGroup:
-    """The fused multi-GPU film exchange over peer memory.  Every rank owns a library-allocated STAGING film; all staging films,
-    the root's merged film and the root's three BGRA images are mapped into every process through CUDA IPC once.
+class ShardedFilmGroup:
+    """The multi-GPU film exchange with NO host synchronisation and a SHARDED result (csrc/drt_exchange.cu).
 
-    scatter=True (default): the render kernel itself does the scatter half -- each rank writes every finished pixel straight
-    into the staging film of the rank that owns the pixel's slice (drt_cuda_render_device_scatter: peer stores over NVLink
-    that hide under the render), then every rank merges the partial films of its slice from LOCAL memory and writes merged
-    planes + images into the root's memory (drt_cuda_film_merge_slices).
-    scatter=False: plain render into the local film, then one kernel per rank that reads all ranks' rows of its slice over
-    NVLink (drt_cuda_film_merge_many).
-    torch.distributed is used only to exchange the 64-byte handles and for the two host barriers around the merge kernel."""
+    Per step every rank enqueues, on one stream and without waiting for anything:
+        render + scatter   each finished pixel goes straight into the staging film of the rank that owns its slice (NVLink)
+        signal             epoch -> this rank's arrival word in every owner's flag block
+        wait               until all ranks' arrival words in the LOCAL flag block hold the epoch
+        merge              the N partial films of the own slice (local memory) -> the own merged slice; the three 8-bit
+                           images of the slice -> the root's image buffer (the only thing that travels after the render)
+        signal             epoch -> this rank's completion word at the root;  root only: wait for all completion words
+    The merged spectral film stays distributed over the owners' slices; read_back() copies a rank's slice into a whole host
+    film over the rank's own PCIe link.  Staging films are double-buffered by epoch parity: step e+1 scatters into the other
+    buffer while slow owners may still be merging step e, and a rank can only reach step e+2 after every rank finished
+    rendering e+1, i.e. after every owner finished merging e.  torch.distributed only exchanges the IPC handles at set-up."""
 
-    def __init__(self, ctx, width, height, root=0, group=None, scatter=True):
-        self.ctx, self.width, self.height, self.root, self.group, self.scatter = ctx, width, height, root, group, scatter
+    ARRIVE, DONE, WORDS = 0, 32, 64      # flag block: arrive[parity][rank] at parity*16 + rank, done[rank] at 32 + rank
+
+    def __init__(self, ctx, width, height, root=0, group=None):
+        self.ctx, self.width, self.height, self.root, self.group = ctx, width, height, root, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         npix = width * height
-        self.slice, parts = slice_partition(npix, self.world)      # pixels per owner; staging holds world * slice pixels
-        rows = -(-self.slice * self.world // width) if scatter else height
-        self.mine = ctx.film_alloc(width, rows)
-        self.merged = ctx.film_alloc(width, height) if self.rank == root else None
+        self.slice, parts = slice_partition(npix, self.world)
+        self.p0, self.p1 = parts[self.rank]
+        rows = -(-self.slice * self.world // width)
+        self.staging = [ctx.film_alloc(width, rows) for _ in range(2)]
+        self.mine = ctx.film_alloc(width, max(1, -(-self.slice // width)))       # this rank's merged slice
+        self.flags = ctx.buffer_alloc(self.WORDS * 4)
         self.images = ctx.buffer_alloc(3 * npix * 4) if self.rank == root else None
+        mine = (ctx.film_ipc_export(self.staging[0]), ctx.film_ipc_export(self.staging[1]), ctx.buffer_ipc_export(self.flags),
+                ctx.buffer_ipc_export(self.images) if self.rank == root else None)
         handles = [None] * self.world
-        dist.all_gather_object(handles, ctx.film_ipc_export(self.mine), group=group)
-        rooted = [(ctx.film_ipc_export(self.merged), ctx.buffer_ipc_export(self.images)) if self.rank == root else None]
-        dist.broadcast_object_list(rooted, src=root, group=group)
-        self._opened = []
-        self.films = []
+        dist.all_gather_object(handles, mine, group=group)
+        self._films, self._bufs = [], []
+        self.peer_staging = [[], []]
+        self.peer_flags = []
         for r in range(self.world):
             if r == self.rank:
-                self.films.append(self.mine)
-            else:
-                f = ctx.film_ipc_open(handles[r])
-                self._opened.append(f)
-                self.films.append(f)
+                self.peer_staging[0].append(self.staging[0]); self.peer_staging[1].append(self.staging[1])
+                self.peer_flags.append(self.flags)
+                continue
+            for par in range(2):
+                f = ctx.film_ipc_open(handles[r][par])
+                self._films.append(f)
+                self.peer_staging[par].append(f)
+            b = ctx.buffer_ipc_open(handles[r][2])
+            self._bufs.append(b)
+            self.peer_flags.append(b)
         if self.rank == root:
-            self.dst, self.img_base = self.merged, self.images
+            self.img_base = self.images
         else:
-            self.dst = ctx.film_ipc_open(rooted[0][0])
-            self._opened.append(self.dst)
-            self.img_base = ctx.buffer_ipc_open(rooted[0][1])
-        if scatter:
-            self.p0, self.p1 = parts[self.rank]
-        else:
-            self.p0, self.p1 = self.rank * npix // self.world, (self.rank + 1) * npix // self.world
+            self.img_base = ctx.buffer_ipc_open(handles[root][3])
+            self._bufs.append(self.img_base)
         self.bgra = [self.img_base + i * npix * 4 for i in range(3)]
-        self.timing = None
+        self.epoch = 0
         dist.barrier(group=group)
 
-    def render(self, params, stream_ptr=None):
-        """This rank's samples of every pixel, into the exchange's staging memory."""
-        if self.scatter:
-            self.ctx.render_device_scatter(params, self.films, self.rank, self.slice, stream=stream_ptr)
-        else:
-            self.ctx.render_device(params, self.mine, accumulate=False, stream=stream_ptr)
+    def step(self, params, stream_ptr=None, mark=None):
+        """One render of this rank's samples of every pixel + the exchange, all enqueued on `stream_ptr`.  `mark(name)` (optional)
+        is called between the phases so that a caller can record events."""
+        self.epoch += 1
+        e, par = self.epoch, self.epoch & 1
+        ctx = self.ctx
+        ctx.render_device_scatter(params, self.peer_staging[par], self.rank, self.slice, stream=stream_ptr)
+        if mark: mark("render")
+        ctx.flags_signal([f + 4 * (self.ARRIVE + 16 * par + self.rank) for f in self.peer_flags], e, stream=stream_ptr)
+        ctx.flags_wait(self.flags + 4 * (self.ARRIVE + 16 * par), self.world, e, stream=stream_ptr)
+        if mark: mark("arrived")
+        ctx.film_merge_slices_local(self.mine, self.staging[par], self.world, self.slice, self.width, self.height, self.p0, self.p1,
+                                    bgra=self.bgra, stream=stream_ptr)
+        if mark: mark("merged")
+        ctx.flags_signal([self.peer_flags[self.root] + 4 * (self.DONE + self.rank)], e, stream=stream_ptr)
+        if self.rank == self.root:
+            ctx.flags_wait(self.flags + 4 * self.DONE, self.world, e, stream=stream_ptr)
+        if mark: mark("done")
+        return 5 + (1 if self.rank == self.root else 0)      # kernels of this library launched by the step
 
-    def merge(self, stream_ptr=None, sync=None):
-        """Call after this rank's render was enqueued.  `sync` = callable that waits for this rank's stream.
-        self.timing (if set to a list) receives (wait for own render, barrier, merge kernel, barrier) in seconds."""
-        import time
-        t0 = time.perf_counter()
-        sync()
-        t1 = time.perf_counter()
-        dist.barrier(group=self.group)          # every rank's partial film is complete (and, scattered, has arrived)
-        t2 = time.perf_counter()
-        if self.scatter:
-            self.ctx.film_merge_slices(self.dst, self.mine, self.world, self.slice, self.width, self.height, self.p0, self.p1,
-                                       bgra=self.bgra, stream=stream_ptr)
-        else:
-            self.ctx.film_merge_many(self.dst, self.films, self.width, self.height, self.p0, self.p1, bgra=self.bgra, stream=stream_ptr)
-        sync()
-        t3 = time.perf_counter()
-        dist.barrier(group=self.group)          # the root's merged film and images are complete
-        if self.timing is not None:
-            self.timing.append((t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
-        return 1
+    def read_back(self, host_film, stream_ptr=None):
+        """This rank's merged slice -> its place in a whole host film (four stream-ordered copies over this rank's PCIe link)."""
+        self.ctx.film_read_slice(self.mine, self.p0, self.p1, host_film, stream=stream_ptr)
+        return (self.p1 - self.p0) * (3 * self.ctx.n + 1) * 4
+
+    def check(self):
+        t = self.ctx.flags_timeouts()
+        if t:
+            raise RuntimeError(f"rank {self.rank}: {t} flag waits gave up (a peer never arrived)")
 
     def close(self):
-        for f in self._opened:
+        for f in self._films:
             try:
                 self.ctx.film_ipc_close(f)
             except Exception:
                 pass
-        if self.rank != self.root:
+        for b in self._bufs:
             try:
-                self.ctx.buffer_ipc_close(self.img_base)
+                self.ctx.buffer_ipc_close(b)
             except Exception:
                 pass
+        for f in self.staging:
+            self.ctx.film_free(f)
         self.ctx.film_free(self.mine)
-        if self.merged is not None:
-            self.ctx.film_free(self.merged)
+        self.ctx.buffer_free(self.flags)
+        if self.images is not None:
             self.ctx.buffer_free(self.images)

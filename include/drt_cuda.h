@@ -103,9 +103,12 @@ int  drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_render_para
 int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *film_host);
 
 /* render_host on several devices of ONE process (what `drt_raytrace --gpus G` calls): contexts[g] live on distinct devices and hold
- * the same scene; the samples [sample_begin, sample_end) are split evenly over them, every device renders its share of every pixel
- * with drt_cuda_render_device_scatter (peer access is enabled between the devices), merges its pixel slice with
- * drt_cuda_film_merge_slices into a film on contexts[0]'s device, and that film is copied to `film_host`.  count = 1 is render_host. */
+ * the same scene; the samples [sample_begin, sample_end) are split evenly over them.  With peer access every device renders its share
+ * of every pixel with drt_cuda_render_device_scatter, announces it with device-side flags (drt_cuda_flags_signal / _wait, no host
+ * synchronisation), merges its own pixel slice locally (drt_cuda_film_merge_slices_local) and copies that slice to `film_host` over its
+ * own PCIe link, all devices at once; staging memory persists between calls on contexts[0].  Without peer access the partial films
+ * are merged one after the other on contexts[0]'s device (slower, same result); with fewer samples than devices the surplus devices
+ * stay idle.  count = 1 is render_host. */
 int  drt_cuda_render_host_multi(drt_cuda_context **contexts, int count, const drt_render_params *params, const drt_film *film_host);
 
 /* Which render kernel the uploaded scene and the geometry precision select, for logs and benchmark lines:
@@ -178,6 +181,32 @@ int  drt_cuda_film_merge_many(drt_cuda_context *ctx, const drt_film *dst_device,
 int  drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film *dst_device, const drt_film *staging_device, int count, uint64_t slice_pixels,
                                 uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
                                 uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
+
+/* The merge half of the scattered exchange with a SHARDED result: like drt_cuda_film_merge_slices, but the merged planes of
+ * [pixel_begin, pixel_end) stay on this device in the caller's slice film (indexed from pixel_begin; a drt_cuda_film_alloc of
+ * ceil(slice_pixels / width) rows), and nothing but the three images (if given; usually the root's memory) leaves the device. */
+int  drt_cuda_film_merge_slices_local(drt_cuda_context *ctx, const drt_film *slice_device, const drt_film *staging_device, int count, uint64_t slice_pixels,
+                                      uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
+                                      uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
+
+/* Four stream-ordered device -> host copies of a merged slice into a WHOLE host film (pinned for the copies to overlap) at the
+ * slice's global pixel positions: every rank reads its own slice back over its own PCIe link. */
+int  drt_cuda_film_read_slice(drt_cuda_context *ctx, const drt_film *slice_device, uint64_t pixel_begin, uint64_t pixel_end,
+                              const drt_film *film_host, void *stream);
+
+/* Device-side arrival flags, the exchange's only synchronisation (no host barrier between the render and the merge):
+ * _signal: one tiny kernel on `stream` that, after everything enqueued before it on the stream has completed, fences system-wide and
+ *          stores `value` to each of the `count` flag words targets[i] (device pointers, local or peer memory);
+ * _wait:   one tiny kernel on `stream` that returns when each of the `count` consecutive LOCAL words at flags_device holds a value
+ *          >= `value` (epochs compared modulo 2^32), so work enqueued after it sees the data the signals announced.  A wait gives up
+ *          after 20 s; _timeouts returns how many did since the context was created (non-zero = a peer never arrived). */
+int  drt_cuda_flags_signal(drt_cuda_context *ctx, uint32_t *const *targets, int count, uint32_t value, void *stream);
+int  drt_cuda_flags_wait(drt_cuda_context *ctx, const uint32_t *flags_device, int count, uint32_t value, void *stream);
+int  drt_cuda_flags_timeouts(drt_cuda_context *ctx, uint32_t *timeouts);
+
+/* Page-locked host memory (portable across devices) for film planes: read-backs into it run as DMA and overlap with rendering. */
+int  drt_cuda_host_alloc(size_t bytes, void **out_host);
+int  drt_cuda_host_free(void *host_ptr);
 
 /* Measured FP32 FMA throughput of this device (TFLOP/s, FFMA counted as 2 flops): the roofline denominator
  * MEASURED_PEAKS.json does not carry.  packed=1 uses fma.rn.f32x2. */

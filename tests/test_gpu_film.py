@@ -210,6 +210,62 @@ def test_scattered_render_and_slice_merge(ctx, ranks, w, h):
         ctx.film_free(f)
 
 
+@pytest.mark.parametrize("ranks,w,h", [(2, 40, 24), (3, 37, 23), (8, 64, 33)])
+def test_sharded_exchange_with_device_flags(ctx, ranks, w, h):
+    """The round-2 exchange emulated on one device, two epochs back to back WITHOUT any host synchronisation in between: per "rank"
+    render + scatter, drt_cuda_flags_signal; per owner drt_cuda_flags_wait, drt_cuda_film_merge_slices_local into the owner's own slice
+    film (sharded result), drt_cuda_film_read_slice into one host film.  The assembled film equals the single render of all samples."""
+    import torch
+    depth, per = 4, 16
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, per * ranks, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    dev = torch.device("cuda", 0)
+    npix = w * h
+    slice_px, parts = film_mod.slice_partition(npix, ranks)
+    rows = -(-slice_px * ranks // w)
+    staging = [[ctx.film_alloc(w, rows) for _ in range(ranks)] for _ in range(2)]       # [parity][owner]
+    slices = [ctx.film_alloc(w, max(1, -(-slice_px // w))) for _ in range(ranks)]
+    flags = [ctx.buffer_alloc(64 * 4) for _ in range(ranks)]                             # per owner: arrive[parity][rank]
+    imgs = [torch.zeros(npix, dtype=torch.int32, device=dev) for _ in range(3)]
+    host = {k: np.zeros((npix, n) if k != "filter" else npix, np.float32) for k in ("sum", "filter", "mean", "m2")}
+    host_film = cuda.Film(host["sum"].ctypes.data, host["filter"].ctypes.data, host["mean"].ctypes.data, host["m2"].ctypes.data)
+    streams = [torch.cuda.Stream() for _ in range(ranks)]                                # one stream per "rank", as on real peers
+    for epoch in (1, 2):
+        par, seed = epoch & 1, 9 + epoch
+        # all signals are enqueued before any wait: on ONE device streams may share a hardware queue, and a wait queued ahead of the
+        # signal it needs would then block it (real peers are separate devices; drt_cuda_render_host_multi enqueues in this order too)
+        for r in range(ranks):
+            sp = streams[r].cuda_stream
+            ctx.render_device_scatter(oracledriver.params(w, h, r * per, (r + 1) * per, depth, cfg.pixel_scheme, seed), staging[par], r, slice_px, stream=sp)
+            ctx.flags_signal([f + 4 * (16 * par + r) for f in flags], epoch, stream=sp)
+        for r in range(ranks):
+            p0, p1 = parts[r]
+            sp = streams[r].cuda_stream
+            ctx.flags_wait(flags[r] + 4 * 16 * par, ranks, epoch, stream=sp)
+            ctx.film_merge_slices_local(slices[r], staging[par][r], ranks, slice_px, w, h, p0, p1, bgra=[t.data_ptr() for t in imgs], stream=sp)
+            if epoch == 2:
+                ctx.film_read_slice(slices[r], p0, p1, host_film, stream=sp)
+    torch.cuda.synchronize()
+    assert ctx.flags_timeouts() == 0
+    whole = film_mod.FilmPlanes(w, h, n, dev)
+    ctx.render_device(oracledriver.params(w, h, 0, per * ranks, depth, cfg.pixel_scheme, 11), whole.as_drt_film())
+    torch.cuda.synchronize()
+    assert np.array_equal(host["filter"], whole.filter.cpu().numpy())
+    for name in ("sum", "mean", "m2"):
+        assert _rel(host[name], getattr(whole, name).cpu().numpy()).max() < 2e-4, name
+    ref_img = torch.zeros(npix, dtype=torch.int32, device=dev)
+    ctx.film_to_rgb(whole.as_drt_film(), w, h, 1, None, ref_img.data_ptr())
+    torch.cuda.synchronize()
+    a, b = imgs[1].cpu().numpy().view(np.uint32), ref_img.cpu().numpy().view(np.uint32)
+    assert max(np.abs(((a >> s) & 255).astype(int) - ((b >> s) & 255).astype(int)).max() for s in (0, 8, 16)) <= 1
+    for f in staging[0] + staging[1] + slices:
+        ctx.film_free(f)
+    for b_ in flags:
+        ctx.buffer_free(b_)
+
+
 @pytest.mark.parametrize("scene", ["cornell_plane_light", "stress_all"])
 def test_large_render_is_finite(ctx, scene):
     """67 M paths through glass, gold and mirrors: no sample may poison a pixel with NaN/inf.  (Regression: with the
