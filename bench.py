@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = --spp samples per pixel IN TOTAL, spp/N per GPU (the north-star workload, default); "
                          "weak = --spp samples per pixel PER GPU (an N*spp image).  The other mode is reported as an extra key.")
+    ap.add_argument("--no-other-scaling", action="store_true", help="skip the extra measurement in the other scaling mode")
     ap.add_argument("--merge", default="sharded", choices=["sharded", "nccl"],
                     help="multi-GPU film combination: sharded = render kernel scatters finished pixels to their owner over NVLink, "
                          "device-side flags, local merge, film stays sharded (default); nccl = 2 all_reduce + 1 reduce")
@@ -434,7 +435,7 @@ def run_b200_arm(a):
 
     # ---- the other scaling mode as an extra figure (N > 1): weak = every GPU renders `spp` samples, strong = `spp` in total
     other = None
-    if world > 1:
+    if world > 1 and not a.no_other_scaling:
         per = a.spp if a.scaling == "strong" else a.spp // world
         if per >= 1:
             p2 = params_for(per)
