@@ -278,7 +278,7 @@ class SharedHostFilm:
     """One page-locked host film that every rank of the node writes its own slice into (POSIX shared memory mapped and
     cudaHostRegister-ed by every process): the host-side destination of the per-rank read-back.  Plumbing only."""
 
-    def __init__(self, torch, dist, npix, n, rank, world):
+    def __init__(self, torch, dist, npix, n, rank, world, pixel_range=None):
         import mmap
         import numpy as np
         self.torch = torch
@@ -295,10 +295,32 @@ class SharedHostFilm:
         self.fd = os.open(self.path, os.O_RDWR)
         self.mm = mmap.mmap(self.fd, self.bytes)
         flat = np.frombuffer(self.mm, dtype=np.float32)
-        self.ptr = flat.ctypes.data
-        rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.bytes, 0)
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        base = flat.ctypes.data
+        # page-lock what this rank's DMA writes: the whole film when it is small, else only the rank's slice of every plane
+        # (one registration of a 13.9 GB film per process is refused by the driver)
+        p0, p1 = pixel_range if pixel_range is not None else (0, npix)
+        if self.bytes <= (2 << 30) or pixel_range is None:
+            ranges = [(0, self.bytes)]
+        else:
+            page = 4096
+            ranges = []
+            for plane, width in ((0, n), (1, n), (2, n)):
+                ranges.append(((plane * npix * n + p0 * width) * 4, (plane * npix * n + p1 * width) * 4))
+            ranges.append(((3 * npix * n + p0) * 4, (3 * npix * n + p1) * 4))
+            ranges = sorted((lo // page * page, min(self.bytes, -(-hi // page) * page)) for lo, hi in ranges if hi > lo)
+            merged = []
+            for lo, hi in ranges:
+                if merged and lo <= merged[-1][1]:
+                    merged[-1] = (merged[-1][0], max(hi, merged[-1][1]))
+                else:
+                    merged.append((lo, hi))
+            ranges = merged
+        self.registered = []
+        for lo, hi in ranges:
+            rc = torch.cuda.cudart().cudaHostRegister(base + lo, hi - lo, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister({hi - lo} bytes) failed: error {int(rc)}")
+            self.registered.append(base + lo)
         self.planes = {"sum": flat[:npix * n].reshape(npix, n), "mean": flat[npix * n:2 * npix * n].reshape(npix, n),
                        "m2": flat[2 * npix * n:3 * npix * n].reshape(npix, n), "filter": flat[3 * npix * n:]}
 
@@ -307,10 +329,11 @@ class SharedHostFilm:
         return cuda.Film(p["sum"].ctypes.data, p["filter"].ctypes.data, p["mean"].ctypes.data, p["m2"].ctypes.data)
 
     def close(self):
-        try:
-            self.torch.cuda.cudart().cudaHostUnregister(self.ptr)
-        except Exception:
-            pass
+        for ptr in self.registered:
+            try:
+                self.torch.cuda.cudart().cudaHostUnregister(ptr)
+            except Exception:
+                pass
         self.planes = None
         if self.owner:
             try:
@@ -447,7 +470,8 @@ def run_b200_arm(a):
     # ---- end to end through host buffers, every step: scene upload (H2D) + render + exchange + film read-back (D2H).
     # N = 1: the C-ABI host-buffer call drt_cuda_render_host.  N > 1 (sharded): every rank reads ITS merged slice back into one
     # shared page-locked host film over its own PCIe link (drt_cuda_film_read_slice); nccl: rank 0 reads the whole film back.
-    host = SharedHostFilm(torch, dist, npix, n, rank, world) if (world == 1 or group is not None) else None
+    host = SharedHostFilm(torch, dist, npix, n, rank, world, (group.p0, group.p1) if group is not None else None) \
+        if (world == 1 or group is not None) else None
     pinned = None
     if host is None and rank == 0:
         pinned = {k: torch.empty(shape, dtype=torch.float32).pin_memory()

@@ -426,7 +426,36 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
                     c[0] = d; c[1] = gl; c[2] = d * e; c[3] = gl * e;
                 }
             }
+            /* the D, G block of the ALLFAST kernel (SpdIndex::plastic2) */
+            const int nchunks = (half_slots + 1) / 2;
+            size_t at2 = (pool.size() + 3) & ~(size_t)3;
+            pool.resize(at2 + (size_t)nchunks * 64, 0.f);
+            index.plastic2[m] = (int)at2;
+            for(int lane = 0; lane < 16; lane += 1)
+                for(int ch = 0; ch < nchunks; ch += 1)
+                {
+                    float *c = &pool[at2 + ((size_t)ch * 16 + lane) * 4];
+                    if(2 * ch + 1 < half_slots)
+                    {
+                        c[0] = val(DRT_SPD_DIFFUSE, 2 * ch, lane); c[1] = val(DRT_SPD_DIFFUSE, 2 * ch + 1, lane);
+                        c[2] = val(DRT_SPD_GLOSSY, 2 * ch, lane);  c[3] = val(DRT_SPD_GLOSSY, 2 * ch + 1, lane);
+                    }
+                    else { c[0] = val(DRT_SPD_DIFFUSE, 2 * ch, lane); c[1] = val(DRT_SPD_GLOSSY, 2 * ch, lane); }
+                }
         }
+        /* the light's emission in slot pairs (SpdIndex::light_pairs) */
+        const int nchunks = (half_slots + 1) / 2;
+        size_t ate = (pool.size() + 3) & ~(size_t)3;
+        pool.resize(ate + (size_t)nchunks * 32, 0.f);
+        index.light_pairs = (int)ate;
+        for(int lane = 0; lane < 16; lane += 1)
+            for(int ch = 0; ch < nchunks; ch += 1)
+            {
+                float *c = &pool[ate + ((size_t)ch * 16 + lane) * 2];
+                int w0 = lane + (2 * ch) * 16, w1 = lane + (2 * ch + 1) * 16;
+                c[0] = (w0 < n && have_e) ? (float)emission[w0] : 0.f;
+                c[1] = (2 * ch + 1 < half_slots && w1 < n && have_e) ? (float)emission[w1] : 0.f;
+            }
     }
 
     std::vector<unsigned char> rgbt(drt_rgb_tables_bytes());
@@ -451,12 +480,15 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_rgb_tables, rgbt.data(), rgbt.size(), cudaMemcpyHostToDevice);
     int nlights = g32->nlights;
-    bool all_fast = nlights == 1;
+    /* ALLFAST carries throughput * E(light): the only emitter a path can run into must then be that light, so an emissive escape
+     * material (a sky, Q19) sends the scene to the general kernel */
+    bool all_fast = nlights == 1 && !scene->materials[scene->escape_material].is_emissive;
     for(int i = 0; i < scene->num_surfaces; i += 1)
     {
         const drt_material *mm = &scene->materials[scene->surfaces[i].material];
         if(!mm->is_black_body && index.plastic[scene->surfaces[i].material] == 0) all_fast = false;
     }
+    if(pool.size() > 65535) all_fast = false;   /* compact records address the blocks with 16-bit word offsets */
     int eval_words = g32->eval_words > 0 ? g32->eval_words : 1;
     delete g32; delete g64;
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "scene upload: %s", cudaGetErrorString(e));

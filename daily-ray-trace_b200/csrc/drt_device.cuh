@@ -93,6 +93,12 @@ struct SpdIndex
      * and for an odd last slot s the last chunk (index nslots - 1) = { D[s], G[s], DE[s], GE[s] }; chunk c of lane l is the
      * float4 at index c*16 + l of the block (nslots*64 words in all). */
     int plastic[DRT_MAX_MATERIALS];
+    /* The ALLFAST kernel carries u = throughput * E (E = emission of the scene's only light) instead of the throughput, so its
+     * blocks hold D and G only: chunk p (a float4 at index p*16 + l) = { D[2p], D[2p+1], G[2p], G[2p+1] }, and for an odd last slot s
+     * the last chunk = { D[s], G[s], 0, 0 }: ceil(nslots / 2) * 64 words.  light_pairs = word offset of E in the same pairing:
+     * float2 { E[2p], E[2p+1] } at index p*16 + l, { E[s], 0 } for an odd last slot. */
+    int plastic2[DRT_MAX_MATERIALS];
+    int light_pairs, pad[3];
 };
 
 struct FilmPtrs { float *sum, *filter, *mean, *m2; };

@@ -772,7 +772,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         {
             /* compact record: four weights per bounce, the 16-bit header (kind | plastic block word offset, a multiple of 4) apart */
             *reinterpret_cast<float4 *>(rec + L.head_words + 4u * nb) = make_float4(wd_n, wg_n, wd_s, wg_s);
-            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)ix.plastic[sm];
+            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)ix.plastic2[sm];
         }
         else if(fast)
         {
@@ -813,6 +813,8 @@ __device__ __forceinline__ void fma2_acc(unsigned long long &acc, unsigned long 
 { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 __device__ __forceinline__ void mul2_by(unsigned long long &x, unsigned long long t)
 { asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(t)); }
+__device__ __forceinline__ void add2_acc(unsigned long long &acc, unsigned long long x)
+{ asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(x)); }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
 { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
@@ -847,12 +849,14 @@ template <int NS> __device__ __forceinline__ void v_add(float (&o)[NS], const fl
     for(int k = 0; k + 1 < NS; k += 2) upk2(add2(pk2(a[k], a[k + 1]), pk2(b[k], b[k + 1])), o[k], o[k + 1]);
     if(NS & 1) o[NS - 1] = a[NS - 1] + b[NS - 1];
 }
+/* a - b as b * (-1) + a: one packed instruction per slot pair (a packed add has no negate modifier, and negating b first costs
+ * one more instruction per slot); exact, so bit-identical to the subtraction */
 template <int NS> __device__ __forceinline__ void v_sub(float (&o)[NS], const float (&a)[NS], const float (&b)[NS])
 {
-    float nb[NS];
+    const unsigned long long m1 = pk2(-1.f, -1.f);
 #pragma unroll
-    for(int k = 0; k < NS; k += 1) nb[k] = -b[k];
-    v_add<NS>(o, a, nb);
+    for(int k = 0; k + 1 < NS; k += 2) upk2(fma2(pk2(b[k], b[k + 1]), m1, pk2(a[k], a[k + 1])), o[k], o[k + 1]);
+    if(NS & 1) o[NS - 1] = a[NS - 1] - b[NS - 1];
 }
 
 /* ------------------------------------------------------------------ phase 2: spectral replay of one record by a HALF warp
@@ -965,39 +969,54 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
     for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(1.f, 1.f); dst2[k] = pk2(0.f, 0.f); }
     if constexpr(ALLFAST)
     {
-        /* compact records (RenderLaunch in drt_device.cuh): header halves from word 2, four weights per bounce */
+        /* compact records (RenderLaunch in drt_device.cuh): header halves from word 2, four weights per bounce.
+         * Every term of the path is throughput * E * (...): the light is the scene's only emitter, so the replay carries
+         * u = throughput * E (thr2 / thr1 below) and needs only the D and G rows:
+         *     radiance += u * (wd_n k * D + wg_n k * G)      u *= wd_s/pdf * D + wg_s/pdf * G      closing emitter: radiance += u */
         const uint16_t *hp = reinterpret_cast<const uint16_t *>(col + REC_HDR16);
         const float4 *wp = reinterpret_cast<const float4 *>(col + L.head_words);
         const uint32_t nshade = nb & 0xffffu;
+        {
+            const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(pool + ix.light_pairs) + lane16;
+#pragma unroll
+            for(int k = 0; k < NP; k += 1) thr2[k] = ep[k * DRT_HALF];
+            if(NS & 1) thr1 = reinterpret_cast<const float *>(ep + NP * DRT_HALF)[0];
+        }
+        uint32_t hdr = hp[0];
+        float4 w = wp[0];   /* wd_n k, wg_n k, wd_s / pdf, wg_s / pdf */
 #pragma unroll 1
         for(uint32_t b = 0; b < nshade; b += 1)
         {
-            const uint32_t hdr = hp[b];
-            const float4 w = wp[b];   /* wd_n k, wg_n k, wd_s / pdf, wg_s / pdf */
             const float4 *blk = reinterpret_cast<const float4 *>(pool + hdr) + lane16;
             const unsigned long long wdn = pk2(w.x, w.x), wgn = pk2(w.y, w.y), wds = pk2(w.z, w.z), wgs = pk2(w.w, w.w);
+            const float w1x = w.x, w1y = w.y, w1z = w.z, w1w = w.w;
+            /* the next bounce's header and weights are in flight while this one is shaded; after the last bounce this reads (and
+             * never uses) up to 16 bytes past the record, which is the next slot or the film parking area, both inside the CTA's
+             * shared memory */
+            hdr = hp[b + 1];
+            w = wp[b + 1];
 #pragma unroll
             for(int k = 0; k < NP; k += 1)
             {
-                const float4 dg = blk[(2 * k) * DRT_HALF], ee = blk[(2 * k + 1) * DRT_HALF];
-                unsigned long long f = fma2(wgn, pk2(ee.z, ee.w), mul2(wdn, pk2(ee.x, ee.y)));
+                const float4 dg = blk[k * DRT_HALF];
+                const unsigned long long d2 = pk2(dg.x, dg.y), g2 = pk2(dg.z, dg.w);
+                unsigned long long f = fma2(wgn, g2, mul2(wdn, d2));
                 fma2_acc(dst2[k], thr2[k], f);
-                unsigned long long t = fma2(wgs, pk2(dg.z, dg.w), mul2(wds, pk2(dg.x, dg.y)));
+                unsigned long long t = fma2(wgs, g2, mul2(wds, d2));
                 mul2_by(thr2[k], t);
             }
             if(NS & 1)
             {
-                const float4 q = blk[(NS - 1) * DRT_HALF];   /* D, G, DE, GE of the last slot */
-                dst1 = fmaf(thr1, fmaf(w.y, q.w, w.x * q.z), dst1);
-                thr1 *= fmaf(w.w, q.y, w.z * q.x);
+                const float2 q = *reinterpret_cast<const float2 *>(blk + NP * DRT_HALF);   /* D, G of the last slot */
+                dst1 = fmaf(thr1, fmaf(w1y, q.y, w1x * q.x), dst1);
+                thr1 *= fmaf(w1w, q.y, w1z * q.x);
             }
         }
-        if(nb >> 16)   /* the path ran into an emitter, cast_ray :453-457 */
+        if(nb >> 16)   /* the path ran into the light, cast_ray :453-457: radiance += throughput * E = u */
         {
-            const float *row = pool_lane + ix.row[(nb >> 16) - 1u][DRT_SPD_EMISSION];
 #pragma unroll
-            for(int k = 0; k < NP; k += 1) fma2_acc(dst2[k], thr2[k], pk2(row[(2 * k) * DRT_HALF], row[(2 * k + 1) * DRT_HALF]));
-            if(NS & 1) dst1 = fmaf(thr1, row[(NS - 1) * DRT_HALF], dst1);
+            for(int k = 0; k < NP; k += 1) add2_acc(dst2[k], thr2[k]);
+            if(NS & 1) dst1 += thr1;
         }
     }
     else
@@ -1389,7 +1408,13 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
                         float c[NS];
                         replay_path<NS, ALLFAST>(rec + slot * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
                         film.add(c);
-                        if(dumping) dump_path<NS>(L.record_dump, L.path_dump, L.path_words, rec + slot * stride, c, (size_t)lp * spp + (paired ? q0 + slot : slot - px * spp), n, lane16);
+                        if(dumping)
+                        {
+                            float cc[NS];   /* a copy whose address is taken only here: c itself stays in registers */
+#pragma unroll
+                            for(int k = 0; k < NS; k += 1) cc[k] = c[k];
+                            dump_path<NS>(L.record_dump, L.path_dump, L.path_words, rec + slot * stride, cc, (size_t)lp * spp + (paired ? q0 + slot : slot - px * spp), n, lane16);
+                        }
                     }
                 }
                 if(!paired)
