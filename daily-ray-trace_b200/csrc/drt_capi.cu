@@ -188,6 +188,40 @@ extern "C" int drt_cuda_analyse_scene(const drt_scene *scene, const drt_camera *
     return DRT_CUDA_OK;
 }
 
+/* Shading class of a material for the compact-record kernels (GeomT::mclass), with the lobe multiplicities of a plastic and the
+ * spectral basis of a specular material.  Every lobe of bdsf.c either always writes (bp_diffuse, bp_glossy, mirror -- which writes
+ * zero on a mismatch --, ct_conductor) or writes only when `in` is the exact reflection / refraction direction (fs_*: Q7, Q8). */
+static int classify_material(const drt_scene *s, int m, int *nd_out, int *ng_out, int *basis_out)
+{
+    const drt_material *mm = &s->materials[m];
+    int nd = 0, ng = 0, nmirror = 0, ncond = 0, ndiel = 0, nct = 0, nother = 0;
+    for(int k = 0; k < mm->num_lobes; k += 1)
+        switch(mm->lobes[k])
+        {
+            case DRT_LOBE_BP_DIFFUSE: nd += 1; break;
+            case DRT_LOBE_BP_GLOSSY: ng += 1; break;
+            case DRT_LOBE_MIRROR: nmirror += 1; break;
+            case DRT_LOBE_FS_CONDUCTOR: ncond += 1; break;
+            case DRT_LOBE_FS_DIELECTRIC_REFLECTANCE: case DRT_LOBE_FS_DIELECTRIC_TRANSMITTANCE: ndiel += 1; break;
+            case DRT_LOBE_CT_CONDUCTOR: nct += 1; break;
+            default: nother += 1; break;
+        }
+    if(nd_out) *nd_out = nd;
+    if(ng_out) *ng_out = ng;
+    if(basis_out) *basis_out = 0;
+    if(mm->num_lobes < 1 || nother) return DRT_CLASS_GENERAL;
+    const bool base_n = s->base_material >= 0 && (s->materials[s->base_material].spd_mask & (1 << DRT_SPD_REFRACT));
+    const bool own_n = (mm->spd_mask & (1 << DRT_SPD_REFRACT)) != 0;
+    if(nd + ng == mm->num_lobes) return DRT_CLASS_PLASTIC;
+    if(nct == mm->num_lobes) return (base_n && own_n) ? DRT_CLASS_ROUGH : DRT_CLASS_GENERAL;
+    if(nmirror + ncond + ndiel == mm->num_lobes && (nmirror != 0) + (ncond != 0) + (ndiel != 0) == 1)
+    {
+        if(basis_out) *basis_out = nmirror ? 0 : ndiel ? 1 : 2;
+        return (nmirror || (base_n && own_n)) ? DRT_CLASS_SPECULAR : DRT_CLASS_GENERAL;
+    }
+    return DRT_CLASS_GENERAL;
+}
+
 template <typename R>
 static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
 {
@@ -293,6 +327,7 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
                 default: break;
             }
         g->bmask[m] = mask;
+        g->mclass[m] = classify_material(s, m, nullptr, nullptr, nullptr);
         int words = __builtin_popcount((unsigned)mask) + ((mask >> BK_COND_MN) & 1);
         if(!mm->is_black_body && words > g->eval_words) g->eval_words = words;
         if(mm->spd_mask & (1 << DRT_SPD_REFRACT))
@@ -426,7 +461,18 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
                     c[0] = d; c[1] = gl; c[2] = d * e; c[3] = gl * e;
                 }
             }
-            /* the D, G block of the ALLFAST kernel (SpdIndex::plastic2) */
+        }
+        /* the D, G blocks of the compact-record kernels (SpdIndex::plastic2): every material whose lobes are all bp_diffuse /
+         * bp_glossy; a lobe listed k times counts k times (bdsf() sums the lobes, daily_ray_trace.c:215-229) */
+        for(int m = 0; m < scene->num_materials; m += 1)
+        {
+            const drt_material *mm = &scene->materials[m];
+            int nd = 0, ng = 0;
+            if(mm->is_black_body || classify_material(scene, m, &nd, &ng, nullptr) != DRT_CLASS_PLASTIC) continue;
+            auto val = [&](int k, int mult, int slot, int lane) -> float {
+                int wl = lane + slot * 16;
+                return (wl < n && (mm->spd_mask & (1 << k))) ? (float)((double)mult * mm->spd[k][wl]) : 0.f;
+            };
             const int nchunks = (half_slots + 1) / 2;
             size_t at2 = (pool.size() + 3) & ~(size_t)3;
             pool.resize(at2 + (size_t)nchunks * 64, 0.f);
@@ -437,10 +483,10 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
                     float *c = &pool[at2 + ((size_t)ch * 16 + lane) * 4];
                     if(2 * ch + 1 < half_slots)
                     {
-                        c[0] = val(DRT_SPD_DIFFUSE, 2 * ch, lane); c[1] = val(DRT_SPD_DIFFUSE, 2 * ch + 1, lane);
-                        c[2] = val(DRT_SPD_GLOSSY, 2 * ch, lane);  c[3] = val(DRT_SPD_GLOSSY, 2 * ch + 1, lane);
+                        c[0] = val(DRT_SPD_DIFFUSE, nd, 2 * ch, lane); c[1] = val(DRT_SPD_DIFFUSE, nd, 2 * ch + 1, lane);
+                        c[2] = val(DRT_SPD_GLOSSY, ng, 2 * ch, lane);  c[3] = val(DRT_SPD_GLOSSY, ng, 2 * ch + 1, lane);
                     }
-                    else { c[0] = val(DRT_SPD_DIFFUSE, 2 * ch, lane); c[1] = val(DRT_SPD_GLOSSY, 2 * ch, lane); }
+                    else { c[0] = val(DRT_SPD_DIFFUSE, nd, 2 * ch, lane); c[1] = val(DRT_SPD_GLOSSY, ng, 2 * ch, lane); }
                 }
         }
         /* the light's emission in slot pairs (SpdIndex::light_pairs) */
@@ -456,6 +502,35 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
                 c[0] = (w0 < n && have_e) ? (float)emission[w0] : 0.f;
                 c[1] = (2 * ch + 1 < half_slots && w1 < n && have_e) ? (float)emission[w1] : 0.f;
             }
+    }
+
+    /* Fresnel input rows (SpdIndex::fres) of every material with a refraction spectrum, for both orientations */
+    if(scene->materials[scene->base_material].spd_mask & (1 << DRT_SPD_REFRACT))
+    {
+        const drt_material *bm = &scene->materials[scene->base_material];
+        const bool base_k = (bm->spd_mask & (1 << DRT_SPD_EXTINCT)) != 0;
+        for(int m = 0; m < scene->num_materials; m += 1)
+        {
+            const drt_material *mm = &scene->materials[m];
+            if(m == scene->base_material || mm->is_black_body || !(mm->spd_mask & (1 << DRT_SPD_REFRACT))) continue;
+            const bool own_k = (mm->spd_mask & (1 << DRT_SPD_EXTINCT)) != 0;
+            for(int side = 0; side < 2; side += 1)
+                for(int k = 0; k < 3; k += 1)
+                {
+                    size_t at = pool.size();
+                    pool.resize(at + (size_t)index.npad, 0.f);
+                    index.fres[m][side][k] = (int)at;
+                    for(int i = 0; i < n; i += 1)
+                    {
+                        /* side 0: incident = base medium, transmitting = this material; side 1: the other way round (Q11) */
+                        const double ir = side ? mm->spd[DRT_SPD_REFRACT][i] : bm->spd[DRT_SPD_REFRACT][i];
+                        const double tr = side ? bm->spd[DRT_SPD_REFRACT][i] : mm->spd[DRT_SPD_REFRACT][i];
+                        const double te = side ? (base_k ? bm->spd[DRT_SPD_EXTINCT][i] : 0.0) : (own_k ? mm->spd[DRT_SPD_EXTINCT][i] : 0.0);
+                        const double eta = tr / ir, kap = te / ir;
+                        pool[at + (size_t)i] = (float)(k == 0 ? ir / tr : k == 1 ? eta * eta - kap * kap : 4.0 * eta * eta * kap * kap);
+                    }
+                }
+        }
     }
 
     std::vector<unsigned char> rgbt(drt_rgb_tables_bytes());
@@ -480,19 +555,24 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_pool, pool.data(), pool.size() * 4, cudaMemcpyHostToDevice);
     if(e == cudaSuccess) e = cudaMemcpy(ctx->d_rgb_tables, rgbt.data(), rgbt.size(), cudaMemcpyHostToDevice);
     int nlights = g32->nlights;
-    /* ALLFAST carries throughput * E(light): the only emitter a path can run into must then be that light, so an emissive escape
-     * material (a sky, Q19) sends the scene to the general kernel */
-    bool all_fast = nlights == 1 && !scene->materials[scene->escape_material].is_emissive;
+    /* The compact-record kernels carry throughput * E(light): the only emitter a path can run into must then be that light, so an
+     * emissive escape material (a sky, Q19) or a second light sends the scene to the general kernel.  all_fast: every surface
+     * material is a plastic (kernel mode 1); classed: plastics, single-basis specular materials and ct_conductor (mode 2). */
+    bool all_fast = nlights == 1 && !scene->materials[scene->escape_material].is_emissive, classed = all_fast;
     for(int i = 0; i < scene->num_surfaces; i += 1)
     {
-        const drt_material *mm = &scene->materials[scene->surfaces[i].material];
-        if(!mm->is_black_body && index.plastic[scene->surfaces[i].material] == 0) all_fast = false;
+        const int m = scene->surfaces[i].material;
+        if(scene->materials[m].is_black_body || scene->surfaces[i].type == DRT_GEO_POINT || scene->surfaces[i].type == DRT_GEO_NONE) continue;
+        const int cls = classify_material(scene, m, nullptr, nullptr, nullptr);
+        if(cls != DRT_CLASS_PLASTIC) all_fast = false;
+        if(cls == DRT_CLASS_GENERAL) classed = false;
     }
-    if(pool.size() > 65535) all_fast = false;   /* compact records address the blocks with 16-bit word offsets */
+    if(getenv("DRT_NO_CLASSED")) classed = all_fast;   /* A/B switch: mixed scenes on the general kernel */
+    if(pool.size() > 65535) all_fast = classed = false;   /* compact records address the blocks with 16-bit word offsets */
     int eval_words = g32->eval_words > 0 ? g32->eval_words : 1;
     delete g32; delete g64;
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "scene upload: %s", cudaGetErrorString(e));
-    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->eval_words = eval_words; ctx->all_fast = all_fast; ctx->pool_words = (uint32_t)pool.size();
+    ctx->n = n; ctx->nslots = index.nslots; ctx->nlights = nlights; ctx->eval_words = eval_words; ctx->all_fast = all_fast; ctx->classed = classed && !all_fast; ctx->pool_words = (uint32_t)pool.size();
     ctx->upload_bytes = sizeof(GeomT<float>) + sizeof(GeomT<double>) + sizeof(SpdIndex) + pool.size() * 4 + rgbt.size();
     ctx->have_scene = true;
     return DRT_CUDA_OK;
@@ -520,11 +600,15 @@ extern "C" int drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, 
     return DRT_CUDA_OK;
 }
 
+/* which instantiation of the render kernel serves the uploaded scene: 0 general (any lobe list, any number of lights; always for the
+ * f64-geometry diagnostic), 1 plastic-only, 2 classed (drt_render.cuh) */
+static int kernel_mode(const drt_cuda_context *ctx) { return ctx->f64_geometry ? 0 : ctx->all_fast ? 1 : ctx->classed ? 2 : 0; }
+
 /* record layout of a render with `max_depth` bounces (RenderLaunch in drt_device.cuh) */
 static void record_layout(const drt_cuda_context *ctx, uint32_t max_depth, RenderLaunch &L)
 {
     L.eval_words = (uint32_t)ctx->eval_words;
-    const bool compact = ctx->all_fast && !ctx->f64_geometry;   /* the ALLFAST kernel and its compact records */
+    const bool compact = kernel_mode(ctx) != 0;   /* the plastic-only and the classed kernel and their compact records */
     L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
     if(L.bounce_words < 8) L.bounce_words = 8;
     L.head_words = 4;
@@ -537,7 +621,7 @@ static void record_layout(const drt_cuda_context *ctx, uint32_t max_depth, Rende
  * allows, and as many CTAs per SM as shared memory and the register budget of the kernel's __launch_bounds__ allow */
 static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int *warps_out, int *ctas_out, size_t *smem_out)
 {
-    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, ctx->all_fast);
+    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, kernel_mode(ctx));
     int warps = full_warps;
     size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots);
     while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); }
@@ -564,8 +648,8 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_rend
     size_t smem = 0;
     if(!launch_shape(ctx, L, &warps, &ctas, &smem)) return fail(DRT_CUDA_E_UNSUPPORTED, "records of max_cast_depth %u do not fit in shared memory", max_depth);
     if(name && name_len)
-        snprintf(name, name_len, "drt::render_kernel<%s,%d,%s,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
-                 (ctx->all_fast && !ctx->f64_geometry) ? "true" : "false", (params->sample_end - params->sample_begin >= 32) ? "true" : "false");
+        snprintf(name, name_len, "drt::render_kernel<%s,%d,%d,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
+                 kernel_mode(ctx), (params->sample_end - params->sample_begin >= 32) ? "true" : "false");
     if(warps_per_cta) *warps_per_cta = warps;
     if(ctas_per_sm) *ctas_per_sm = ctas;
     return DRT_CUDA_OK;
@@ -636,7 +720,7 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     L.stats = ctx->d_stats;
     L.task_counter = ctx->d_counter_ring + (ctx->counter_launches++ % DRT_RING);
     CU(cudaMemsetAsync(L.task_counter, 0, sizeof(unsigned int), stream));
-    cudaError_t e = drt_launch_render(L, ctx->f64_geometry, ctx->all_fast, ctx->nslots, (int)grid, warps, smem, stream);
+    cudaError_t e = drt_launch_render(L, ctx->f64_geometry, kernel_mode(ctx), ctx->nslots, (int)grid, warps, smem, stream);
     if(e != cudaSuccess) return fail(DRT_CUDA_E_CUDA, "render kernel launch: %s", cudaGetErrorString(e));
     ctx->launches += 1;
     ctx->last_launches = 1;

@@ -10,8 +10,8 @@
 #include "drt_cuda.h"
 #include "drt_device.cuh"
 
-cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-int         drt_render_cta_warps(bool f64_geometry, bool all_fast);
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int mode, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
+int         drt_render_cta_warps(bool f64_geometry, int mode);
 size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots);
 void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);
@@ -39,6 +39,7 @@ struct drt_cuda_context
     int    n = 0, nslots = 0, nlights = 0, eval_words = 1;
     bool   hit_bound = false;      /* hit_u/v: film-plane bound (in pixel units of the uploaded camera) of everything a camera ray can hit */
     double hit_u0 = 0, hit_u1 = 0, hit_v0 = 0, hit_v1 = 0;
+    bool   classed = false;       /* plastics + specular / rough-conductor materials under one light: the classed compact-record kernel */
     bool   all_fast = false;      /* every surface material has a plastic block (SpdIndex::plastic): the specialised kernel applies */
     void  *d_geom32 = nullptr, *d_geom64 = nullptr;
     SpdIndex *d_index = nullptr;

@@ -22,6 +22,9 @@
 #ifndef DRT_FAST_WARPS
 #define DRT_FAST_WARPS 14     /* warps per CTA of the ALLFAST kernel: 2 CTAs x 14 warps x 72 registers per SM (measured: 8 warps 6.7, 12: 9.70, 14: 9.79, 16: 9.65 G paths/s) */
 #endif
+#ifndef DRT_CLASSED_WARPS
+#define DRT_CLASSED_WARPS 12   /* warps per CTA of the classed kernel */
+#endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS
 #define DRT_MIN_CTAS 2        /* resident CTAs per SM the render kernels are compiled for (__launch_bounds__) */
@@ -30,6 +33,7 @@
 /* Spectral basis a BSDF evaluation is expressed in (eval_weights in drt_kernels.cu).  A material's lobe list fixes
  * which of the seven can ever be non-zero (bmask); only those weights are stored in a path record, in this order,
  * followed by the micro-normal cosine when BK_COND_MN is present. */
+enum { DRT_CLASS_PLASTIC = 0, DRT_CLASS_SPECULAR = 1, DRT_CLASS_ROUGH = 2, DRT_CLASS_GENERAL = 3 };
 enum { BK_CONST = 0, BK_DIFFUSE, BK_GLOSSY, BK_MIRROR, BK_DIEL_R, BK_COND_ON, BK_COND_MN, BK_COUNT };
 
 /* one surface as four 16-byte (f32) / 32-byte (f64) vectors, so that the intersection loop issues vector shared-memory loads */
@@ -70,6 +74,14 @@ struct GeomT
     R   light_pdf[DRT_MAX_SURFACES];
     /* materials */
     int mflags[DRT_MAX_MATERIALS];   /* bit0 is_black_body, bit1 is_emissive */
+    /* Shading class of the compact-record kernels (DRT_CLASS_*): what one bounce on this material needs in its 4-word record.
+     *   PLASTIC   lobes all bp_diffuse / bp_glossy: NEE and sampled-direction weights (w_d, w_g) of the material's D, G block
+     *   SPECULAR  lobes all match-gated (mirror, fs_conductor, fs_dielectric_R / _T) over ONE spectral basis X (mirror spectrum,
+     *             dielectric R(on_dot) or conductor F(on_dot)): next-event estimation contributes nothing, the sampled direction
+     *             multiplies the throughput by c0 + c1 X
+     *   ROUGH     ct_conductor only: w F(cos) with the micro-normal cosine of each evaluation
+     *   GENERAL   anything else (the general kernel) */
+    int mclass[DRT_MAX_MATERIALS];
     int bmask[DRT_MAX_MATERIALS];    /* bit k: basis kind k can be produced by this material's lobe list */
     int nlobes[DRT_MAX_MATERIALS], dirf[DRT_MAX_MATERIALS];
     unsigned char lobes[DRT_MAX_MATERIALS][DRT_MAX_LOBES];
@@ -99,6 +111,12 @@ struct SpdIndex
      * float2 { E[2p], E[2p+1] } at index p*16 + l, { E[s], 0 } for an odd last slot. */
     int plastic2[DRT_MAX_MATERIALS];
     int light_pairs, pad[3];
+    /* Fresnel inputs per wavelength, precomputed in f64 at upload for the two orientations a surface can be met in (0: from the
+     * base medium, 1: from inside, Q11), as plain pool rows (word offsets; 0 = absent): with ir / tr / te the incident refraction,
+     * transmitting refraction and transmitting extinction of bdsf.c:44-101,
+     *   [0] rel  = ir / tr                                    dielectric (fresnel_dielectric_rel)
+     *   [1] condA = (tr / ir)^2 - (te / ir)^2   [2] condB = 4 (tr / ir)^2 (te / ir)^2          conductor (fresnel_conductor_ab) */
+    int fres[DRT_MAX_MATERIALS][2][3];
 };
 
 struct FilmPtrs { float *sum, *filter, *mean, *m2; };
@@ -125,11 +143,16 @@ struct DeviceStats
  *                         [1] w_diffuse * k  [2] w_glossy * k   (next-event estimation, 0 when the light is hidden)
  *                         [4] w_diffuse / pdf [5] w_glossy / pdf (sampled direction)
  *   bounce_words is a multiple of 4 and at least 8.
- * Compact records of the ALLFAST kernel (every surface material a two-lobe plastic, one light):
- *   word 0, 1         number of bounce records, vignette factor
- *   from word 2       one 16-bit header per bounce: kind(2) | plastic block word offset (a multiple of 4), or kind | material<<2
- *                     for a path that ran into an emitter
- *   from head_words   per bounce { w_diffuse k, w_glossy k (next-event estimation), w_diffuse / pdf, w_glossy / pdf (sampled direction) } */
+ * Compact records of the plastic-only and the classed kernel (one light, which is the scene's only emitter):
+ *   word 0, 1         number of bounce records | (emitter material + 1) << 16, vignette factor
+ *   from word 2       one 16-bit header per bounce: class (bits 0-1, DRT_CLASS_*) and
+ *                       PLASTIC   the word offset of the material's D, G block (SpdIndex::plastic2, a multiple of 4: class bits 0)
+ *                       SPECULAR  basis << 2 (0 mirror spectrum, 1 dielectric R, 2 conductor F) | inside << 4 | material << 5
+ *                       ROUGH     inside << 4 | material << 5
+ *   from head_words   per bounce four words:
+ *                       PLASTIC   { w_diffuse k, w_glossy k (next-event estimation), w_diffuse / pdf, w_glossy / pdf (sampled direction) }
+ *                       SPECULAR  { c0 / pdf, c1 / pdf, on_dot, - }
+ *                       ROUGH     { w k, micro-normal cosine (next-event estimation; w = 0 when the light is hidden), w / pdf, cosine } */
 struct RenderLaunch
 {
     const void     *geom;          /* GeomT<float> or GeomT<double> in global memory */

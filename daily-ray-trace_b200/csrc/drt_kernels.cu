@@ -6,19 +6,25 @@
 #include "drt_device.cuh"
 
 cudaError_t drt_launch_render_f32_fast(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
+cudaError_t drt_launch_render_f32_classed(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
 cudaError_t drt_launch_render_f32_general(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
 cudaError_t drt_launch_render_f64(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
 
 /* f64 geometry is the branch-flip diagnostic: it always runs the general kernel */
-cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, bool all_fast, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
+cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int mode, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
     const bool paired = L.pixels_per_task == 1;
     if(f64_geometry) return drt_launch_render_f64(L, paired, nslots, grid, warps, smem, stream);
-    return all_fast ? drt_launch_render_f32_fast(L, paired, nslots, grid, warps, smem, stream)
-                    : drt_launch_render_f32_general(L, paired, nslots, grid, warps, smem, stream);
+    return mode == 1 ? drt_launch_render_f32_fast(L, paired, nslots, grid, warps, smem, stream)
+         : mode == 2 ? drt_launch_render_f32_classed(L, paired, nslots, grid, warps, smem, stream)
+                     : drt_launch_render_f32_general(L, paired, nslots, grid, warps, smem, stream);
 }
 
-int drt_render_cta_warps(bool f64_geometry, bool all_fast) { return (!f64_geometry && all_fast) ? DRT_FAST_WARPS : DRT_CTA_WARPS; }
+int drt_render_cta_warps(bool f64_geometry, int mode)
+{
+    if(f64_geometry) return DRT_CTA_WARPS;
+    return mode == 1 ? DRT_FAST_WARPS : mode == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS;
+}
 
 size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots)
 {

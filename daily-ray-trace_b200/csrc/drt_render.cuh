@@ -648,10 +648,12 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 /* ------------------------------------------------------------------ phase 1: trace one path, emit its record
  * `rec` points at this lane's record (16-byte aligned).  Returns the termination-histogram bin and a class bit. */
 
-template <typename R, bool ALLFAST>
+template <typename R, int MODE>
 __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec,
                                                uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
 {
+    constexpr bool ALLFAST = MODE != 0;    /* compact records: the plastic-only kernel (1) and the classed kernel (2) */
+    constexpr bool CLASSED = MODE == 2;
     Rng rng;
     rng.begin(L.seed, y * L.width + x, sample);
 
@@ -707,13 +709,17 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
             break;
         }
         shaded += 1;
-        /* two-lobe plastic: two weights per evaluation, computed inline; under a single light the bounce also has the fixed
-         * 8-word "fast" record.  Shadow rays, direction sampling and the weight arithmetic are shared by all materials so
-         * that a warp whose lanes sit on different materials does not run them twice. */
+        /* Plastic (bp_diffuse + bp_glossy): two weights per evaluation, computed inline; under a single light the bounce also has a
+         * fixed-size "fast" record (8 words in the general kernel, 4 in the compact-record kernels).  Shadow rays, direction sampling
+         * and the weight arithmetic are shared by all materials so that a warp whose lanes sit on different materials does not run
+         * them twice.  The classed kernel (MODE 2) gives specular and rough-conductor bounces 4-word records too (drt_device.cuh). */
         const int sm = h.surf_mat;
-        const bool plastic = ALLFAST || (g.bmask[sm] == BMASK_PLASTIC && g.nlobes[sm] == 2);
+        const int cls = CLASSED ? g.mclass[sm] : DRT_CLASS_PLASTIC;
+        const bool plastic = ALLFAST ? (cls == DRT_CLASS_PLASTIC) : (g.bmask[sm] == BMASK_PLASTIC && g.nlobes[sm] == 2);
         const bool fast = ALLFAST || (plastic && ix.plastic[sm] != 0);
         const int nlights = ALLFAST ? 1 : g.nlights;
+        float *recw = rec + L.head_words + 4u * nb;   /* this bounce's four words in a compact record */
+        if(CLASSED && cls == DRT_CLASS_ROUGH) { recw[0] = 0.f; recw[1] = 1.f; }   /* the light may turn out hidden */
         /* K3: direct_light_contribution, :272-332 -- every emissive surface in index order; draws come before visibility */
         uint32_t vis_mask = 0;
         float wd_n = 0.f, wg_n = 0.f;
@@ -756,6 +762,12 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                     plastic_weights<R>(g, sm, h.nrm, h.out, ldir, fast ? (float)k : 1.f, wd_n, wg_n);
                     if(!fast) { rec[e] = wd_n; rec[e + 1] = wg_n; }
                 }
+                else if(CLASSED)
+                {
+                    /* rough conductor: w k and the micro-normal cosine; a specular material contributes nothing to next-event
+                     * estimation (its lobes are gated on the exact reflection / refraction direction, Q8) */
+                    if(cls == DRT_CLASS_ROUGH) eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, (float)k, recw, 0);
+                }
                 else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, 1.f, rec, e);
                 if(!fast) rec[e + ew] = (float)k;
                 vis_mask |= 1u << j;
@@ -767,12 +779,38 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         const uint32_t es = base + 2 + (ew + 1) * (uint32_t)nlights;
         float wd_s = 0.f, wg_s = 0.f;
         if(plastic) plastic_weights<R>(g, sm, h.nrm, h.out, in, (float)inv_pdf, wd_s, wg_s);
-        else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, es);
+        else if(!CLASSED) eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, es);
         if(ALLFAST)
         {
-            /* compact record: four weights per bounce, the 16-bit header (kind | plastic block word offset, a multiple of 4) apart */
-            *reinterpret_cast<float4 *>(rec + L.head_words + 4u * nb) = make_float4(wd_n, wg_n, wd_s, wg_s);
-            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)ix.plastic2[sm];
+            uint32_t hdr16;
+            if(plastic)
+            {
+                /* four weights per bounce; the 16-bit header (class 0 | D, G block word offset, a multiple of 4) apart */
+                *reinterpret_cast<float4 *>(recw) = make_float4(wd_n, wg_n, wd_s, wg_s);
+                hdr16 = (uint32_t)ix.plastic2[sm];
+            }
+            else
+            {
+                general = 1;   /* sorts the path among those whose replay leaves the plastic loop */
+                const uint32_t inside = (h.inc_mat != g.base_mat) ? 1u : 0u;
+                if(cls == DRT_CLASS_ROUGH)
+                {
+                    eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, recw, 2);
+                    hdr16 = (uint32_t)DRT_CLASS_ROUGH | (inside << 4) | ((uint32_t)sm << 5);
+                }
+                else
+                {
+                    /* c0 + c1 X over the material's one spectral basis X: the evaluator stores the weights its lobe list can
+                     * produce in basis order, the constant (of fs_dielectric_transmittance's 1 - R) first */
+                    const int mask = g.bmask[sm];
+                    eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, recw, 0);
+                    if(!(mask & (1 << BK_CONST))) { recw[1] = recw[0]; recw[0] = 0.f; }
+                    recw[2] = (float)h.on_dot;
+                    const uint32_t basis = (mask & (1 << BK_MIRROR)) ? 0u : (mask & (1 << BK_DIEL_R)) ? 1u : 2u;
+                    hdr16 = (uint32_t)DRT_CLASS_SPECULAR | (basis << 2) | (inside << 4) | ((uint32_t)sm << 5);
+                }
+            }
+            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)hdr16;
         }
         else if(fast)
         {
@@ -951,6 +989,75 @@ static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *
     return st;
 }
 
+/* ------------------------------------------------------------------ classed kernel: specular and rough-conductor bounces
+ *
+ * Fresnel terms on the rows precomputed at upload (SpdIndex::fres): the same formulas as fresnel_dielectric / fresnel_conductor
+ * above with the per-wavelength ratios taken out (rel = ir / tr;  A = eta^2 - kappa^2, B = 4 eta^2 kappa^2 with eta = tr / ir,
+ * kappa = te / ir), dividing numerator and denominator of the dielectric amplitudes by tr (bdsf.c:44-101, Q9 kept). */
+__device__ __forceinline__ float fresnel_dielectric_rel(float rel, float inc_cos)
+{
+    const float inc_sin_sq = 1.f - inc_cos * inc_cos;
+    const float ts_sin_sq = rel * rel * inc_sin_sq;
+    if(ts_sin_sq >= 1.f) return 1.f;
+    const float ts_cos = r_sqrt_fast(1.f - ts_sin_sq * ts_sin_sq);
+    const float a = rel * ts_cos, b = rel * inc_cos;
+    const float par = r_div(inc_cos - a, inc_cos + a);
+    const float per = r_div(b - ts_cos, b + ts_cos);
+    return 0.5f * (par * par + per * per);
+}
+__device__ __forceinline__ float fresnel_conductor_ab(float A, float B, float inc_cos)
+{
+    const float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
+    const float r = A - sin_sq;
+    const float apb_sq = r_sqrt_fast(fmaf(r, r, B));
+    const float a = r_sqrt_fast(fmaxf(0.5f * (apb_sq + r), 0.f));   /* clamp: see fresnel_conductor */
+    const float s = apb_sq + cos_sq;
+    const float t = 2.f * a * inc_cos;
+    const float u = fmaf(cos_sq, apb_sq, sin_sq * sin_sq);
+    const float v = t * sin_sq;
+    const float par = r_div(s - t, s + t);
+    const float per = r_div(par * (u - v), u + v);
+    return 0.5f * (par + per);
+}
+
+/* u = throughput * E and the radiance of a path, as the replay loop of the compact-record kernels carries them */
+template <int NS> struct Carry { float u[NS], d[NS]; };
+
+/* One bounce of class SPECULAR or ROUGH (record layout: RenderLaunch in drt_device.cuh), out of line: cold relative to the
+ * plastic loop, and the Fresnel formulas exist once. */
+template <int NS>
+static __device__ __noinline__ Carry<NS> shade_special(uint32_t hdr, float4 w, const float *pool_lane, const SpdIndex &ix, Carry<NS> st)
+{
+    const int cls = (int)(hdr & 3u), inside = (int)((hdr >> 4) & 1u), mat = (int)((hdr >> 5) & 31u);
+    if(cls == DRT_CLASS_SPECULAR)
+    {
+        const uint32_t basis = (hdr >> 2) & 3u;
+        const float *x0 = pool_lane + (basis == 0u ? ix.row[mat][DRT_SPD_MIRROR] : basis == 1u ? ix.fres[mat][inside][0] : ix.fres[mat][inside][1]);
+        const float *x1 = pool_lane + ix.fres[mat][inside][2];
+#pragma unroll
+        for(int k = 0; k < NS; k += 1)
+        {
+            float x = x0[k * DRT_HALF];
+            if(basis == 1u) x = fresnel_dielectric_rel(x, w.z);
+            else if(basis == 2u) x = fresnel_conductor_ab(x, x1[k * DRT_HALF], w.z);
+            st.u[k] *= fmaf(w.y, x, w.x);   /* throughput *= (c0 + c1 X) / pdf, cast_ray :467-469 */
+        }
+    }
+    else
+    {
+        const float *ra = pool_lane + ix.fres[mat][inside][1], *rb = pool_lane + ix.fres[mat][inside][2];
+        if(w.x != 0.f)   /* the light is visible: radiance += u * (w k F(cos_n)), :458-462 */
+        {
+#pragma unroll
+            for(int k = 0; k < NS; k += 1)
+                st.d[k] = fmaf(st.u[k], w.x * fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], w.y), st.d[k]);
+        }
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) st.u[k] *= w.z * fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], w.w);
+    }
+    return st;
+}
+
 /* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from the record `col` (nb >= 1 bounces);
  * returns the path contribution already multiplied by the vignette factor (:612-615).
  * Throughput and radiance are held as f32x2 register pairs for wavelength slots (0,1), (2,3), ... plus one scalar for an
@@ -958,10 +1065,11 @@ static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *
  *     radiance   += throughput * (wd_n k * DE + wg_n k * GE)        (NEE: bdsf * emission * k, :322-327; weights are 0 when shadowed)
  *     throughput *= wd_s/pdf * D + wg_s/pdf * G                      (:467-469)
  * with D, G, DE = D*E, GE = G*E fetched from the material's interleaved plastic block by 16-byte loads. */
-template <int NS, bool ALLFAST, typename G>
+template <int NS, int MODE, typename G>
 __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool, const float *pool_lane,
                                             uint32_t lane16, const RenderLaunch &L, float (&c)[NS])
 {
+    constexpr bool ALLFAST = MODE != 0, CLASSED = MODE == 2;
     constexpr int NP = NS / 2;
     unsigned long long thr2[NP > 0 ? NP : 1], dst2[NP > 0 ? NP : 1];
     float thr1 = 1.f, dst1 = 0.f;
@@ -987,6 +1095,23 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
 #pragma unroll 1
         for(uint32_t b = 0; b < nshade; b += 1)
         {
+            if constexpr(CLASSED)
+            {
+                if(hdr & 3u)   /* a specular or rough-conductor bounce */
+                {
+                    Carry<NS> st;
+#pragma unroll
+                    for(int k = 0; k < NP; k += 1) { upk2(thr2[k], st.u[2 * k], st.u[2 * k + 1]); upk2(dst2[k], st.d[2 * k], st.d[2 * k + 1]); }
+                    if(NS & 1) { st.u[NS - 1] = thr1; st.d[NS - 1] = dst1; }
+                    st = shade_special<NS>(hdr, w, pool_lane, ix, st);
+#pragma unroll
+                    for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(st.u[2 * k], st.u[2 * k + 1]); dst2[k] = pk2(st.d[2 * k], st.d[2 * k + 1]); }
+                    if(NS & 1) { thr1 = st.u[NS - 1]; dst1 = st.d[NS - 1]; }
+                    hdr = hp[b + 1];
+                    w = wp[b + 1];
+                    continue;
+                }
+            }
             const float4 *blk = reinterpret_cast<const float4 *>(pool + hdr) + lane16;
             const unsigned long long wdn = pk2(w.x, w.x), wgn = pk2(w.y, w.y), wds = pk2(w.z, w.z), wgs = pk2(w.w, w.w);
             const float w1x = w.x, w1y = w.y, w1z = w.z, w1w = w.w;
@@ -1219,9 +1344,10 @@ static __device__ __noinline__ void dump_path(float *record_dump, float *path_du
 #define DRT_PARK_GENERAL 0   /* park the film of the general kernel too (pays off only if that buys resident warps) */
 #endif
 /* PAIRED: one pixel per task with all its samples (spp >= 32) against 32/spp whole pixels per task; see the task loop. */
-template <typename R, int NS, bool ALLFAST, bool PAIRED>
-__global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_THREADS, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
+template <typename R, int NS, int MODE, bool PAIRED>
+__global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS) * DRT_WARP, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
 {
+    constexpr bool ALLFAST = MODE != 0;   /* compact records, film parked in shared memory while tracing */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
     size_t off = (sizeof(GeomT<R>) + 15) & ~size_t(15);
@@ -1339,7 +1465,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
                 }
                 else
                 {
-                    uint32_t r = trace_path<R, ALLFAST>(g, ix, L, rec + lane * stride, x, y, L.sample_begin + my_s, tally);
+                    uint32_t r = trace_path<R, MODE>(g, ix, L, rec + lane * stride, x, y, L.sample_begin + my_s, tally);
                     bin = r & 255u; general = r >> 8;
                 }
             }
@@ -1406,7 +1532,7 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
                     if(pos < lo + per_px)
                     {
                         float c[NS];
-                        replay_path<NS, ALLFAST>(rec + slot * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
+                        replay_path<NS, MODE>(rec + slot * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
                         film.add(c);
                         if(dumping)
                         {
@@ -1451,15 +1577,15 @@ __global__ void __launch_bounds__(ALLFAST ? DRT_FAST_WARPS * DRT_WARP : DRT_CTA_
 
 /* ------------------------------------------------------------------ launch helper of the instantiating translation units */
 
-template <typename R, bool ALLFAST, bool PAIRED>
+template <typename R, int MODE, bool PAIRED>
 static cudaError_t drt_launch_render_ns(const RenderLaunch &L, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
 #define DRT_LAUNCH(NS) do { \
-        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS, ALLFAST, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if(e != cudaSuccess) return e; \
-        e = cudaFuncSetAttribute(drt::render_kernel<R, NS, ALLFAST, PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         if(e != cudaSuccess) return e; \
-        drt::render_kernel<R, NS, ALLFAST, PAIRED><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
+        drt::render_kernel<R, NS, MODE, PAIRED><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
     switch(nslots)   /* wavelength slots per lane of a half warp: N <= 32, 48, 80, 128 */
     {
         case 2: DRT_LAUNCH(2); break;

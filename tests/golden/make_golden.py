@@ -34,6 +34,9 @@ CASES = [
     ("rotated_room", 64, 48, (20, 12, 44, 28), 2, 5, "pixel_random", 18),
     # pinhole camera + EMISSIVE escape material (Q19 environment light): the tile straddles the scene's screen-space edge
     ("sky_cornell", 64, 48, (0, 8, 24, 24), 2, 4, "pixel_random", 19),
+    # one light, pinhole: every material class of the classed compact-record kernel (plastics with repeated / single lobes and a
+    # uniform-hemisphere sampler, mirror, fs_conductor, glass R+T, transmittance only, ct_conductor)
+    ("classed_all", 64, 48, (8, 8, 56, 32), 2, 6, "pixel_random", 20),
 ]
 
 

@@ -132,3 +132,19 @@ def test_depth_zero_and_no_samples_give_black_films(ctx, scene):
     film = ctx.render_host(oracledriver.params(w, h, 7, 7, 4, cfg.pixel_scheme, 3))       # no samples at all
     assert all(not film[k].any() for k in ("sum", "mean", "m2", "filter"))
     assert ctx.stats().paths == 0
+
+
+@pytest.mark.parametrize("scene,mode", [("init_cornell", 1), ("cornell_large_box", 1), ("rotated_room", 1), ("cornell_plane_light", 2), ("classed_all", 2),
+                                        ("stress_all", 0), ("sky_cornell", 0)])
+def test_kernel_selection(ctx, scene, mode):
+    """Which instantiation serves a scene (drt_cuda_render_kernel_info): 1 = plastic-only, 2 = classed (plastics + specular + rough
+    conductor under one light), 0 = general (several lights, an emissive escape material, other lobe lists); f64 geometry -> general."""
+    cfg, tables, sc, camera = common.load(scene, 32, 32, 32, 4)
+    ctx.upload_scene(sc, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    prm = oracledriver.params(32, 32, 0, 32, 4, cfg.pixel_scheme, 1)
+    name, warps, ctas = ctx.render_kernel_info(prm)
+    assert name == f"drt::render_kernel<float,5,{mode},true>", name
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+    assert ctx.render_kernel_info(prm)[0] == "drt::render_kernel<double,5,0,true>"
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)

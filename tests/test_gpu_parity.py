@@ -28,6 +28,7 @@ CASES = [
     ("stress_all", 64, 48, (0, 0, 64, 48), 5, 6, "pixel_random"),
     ("rotated_room", 64, 48, (0, 0, 64, 48), 4, 5, "pixel_random"),     # all-plastic kernel on planes in general position
     ("sky_cornell", 64, 48, (0, 0, 64, 48), 3, 4, "pixel_random"),      # pinhole + emissive escape material (Q19): no pixel may be culled
+    ("classed_all", 64, 48, (0, 0, 64, 48), 6, 6, "pixel_random"),      # classed kernel: plastics, mirror, fs_conductor, glass, transmit, ct_conductor
 ]
 
 

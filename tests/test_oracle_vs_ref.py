@@ -21,6 +21,7 @@ CASES = [
     ("stress_all", 32, 24, 4, 6, "pixel_random"),
     ("rotated_room", 32, 24, 3, 5, "pixel_random"),      # planes in general position, a tilted card and a ball inside, plane light
     ("sky_cornell", 32, 24, 3, 4, "pixel_random"),       # pinhole camera + emissive escape material (Q19), all-plastic walls
+    ("classed_all", 32, 24, 4, 6, "pixel_random"),       # every material class of the classed kernel under one light
 ]
 
 

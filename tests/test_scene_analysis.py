@@ -16,7 +16,7 @@ cuda = importlib.import_module("daily-ray-trace_b200.cuda")
 film = importlib.import_module("daily-ray-trace_b200.film")
 
 SCENES = ["init_cornell", "cornell_plane_light", "cornell_large_box", "cornell_downward", "first_scene", "example_scene", "stress_all",
-          "rotated_room"]
+          "rotated_room", "classed_all"]
 
 
 @pytest.mark.parametrize("w,h", [(64, 48), (40, 56), (33, 33)])
