@@ -328,6 +328,31 @@ static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
             }
         g->bmask[m] = mask;
         g->mclass[m] = classify_material(s, m, nullptr, nullptr, nullptr);
+        if(g->mclass[m] == DRT_CLASS_SPECULAR)
+            for(int match = 0; match < 3; match += 1)
+            {
+                /* the lobe walk of bdsf() (daily_ray_trace.c:215-229) over the match-gated lobes: a lobe that does not write leaves
+                 * the previous lobe's value in the scratch spectrum, which is added again (Q7) */
+                const bool refl = match == 1, trans = match == 2;
+                double cur_c = 0.0, cur_x = 0.0, acc_c = 0.0, acc_x = 0.0;
+                for(int k = 0; k < mm->num_lobes; k += 1)
+                {
+                    bool wrote = false; double val = 0.0, val_c = 0.0;
+                    switch(mm->lobes[k])
+                    {
+                        case DRT_LOBE_MIRROR: wrote = true; val = refl ? 1.0 : 0.0; break;
+                        case DRT_LOBE_FS_CONDUCTOR: case DRT_LOBE_FS_DIELECTRIC_REFLECTANCE: wrote = refl; val = 1.0; break;
+                        case DRT_LOBE_FS_DIELECTRIC_TRANSMITTANCE: wrote = trans; val = -1.0; val_c = 1.0; break;
+                        default: break;
+                    }
+                    if(wrote) { cur_x = val; cur_c = val_c; }
+                    acc_c += cur_c; acc_x += cur_x;
+                }
+                g->spec_c[m][match][0] = (float)acc_c; g->spec_c[m][match][1] = (float)acc_x;
+            }
+        int nct = 0;
+        for(int k = 0; k < mm->num_lobes && k < DRT_MAX_LOBES; k += 1) nct += mm->lobes[k] == DRT_LOBE_CT_CONDUCTOR;
+        g->ct_mult[m] = (float)nct;
         int words = __builtin_popcount((unsigned)mask) + ((mask >> BK_COND_MN) & 1);
         if(!mm->is_black_body && words > g->eval_words) g->eval_words = words;
         if(mm->spd_mask & (1 << DRT_SPD_REFRACT))

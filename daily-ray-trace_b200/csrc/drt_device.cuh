@@ -82,6 +82,11 @@ struct GeomT
      *   ROUGH     ct_conductor only: w F(cos) with the micro-normal cosine of each evaluation
      *   GENERAL   anything else (the general kernel) */
     int mclass[DRT_MAX_MATERIALS];
+    /* SPECULAR: every lobe is gated on `in` being the exact reflection (match 1) or refraction (match 2) direction, so the
+     * bdsf() sum over the lobe list -- stale scratch values included, Q7 -- is one of three constant pairs (c0, c1) of
+     * c0 + c1 X, tabulated at upload by walking the lobe list exactly as eval_weights_general does: spec_c[m][match] */
+    float spec_c[DRT_MAX_MATERIALS][3][2];
+    float ct_mult[DRT_MAX_MATERIALS];   /* ROUGH: how many times ct_conductor_bdsf is listed */
     int bmask[DRT_MAX_MATERIALS];    /* bit k: basis kind k can be produced by this material's lobe list */
     int nlobes[DRT_MAX_MATERIALS], dirf[DRT_MAX_MATERIALS];
     unsigned char lobes[DRT_MAX_MATERIALS][DRT_MAX_LOBES];

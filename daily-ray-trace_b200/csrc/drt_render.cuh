@@ -455,6 +455,30 @@ __device__ __forceinline__ void plastic_weights(const GeomT<R> &g, int m, V3<R> 
     wd = (float)((R(1) / Num<R>::pi()) * cos_in) * scale;
     wg = (float)(coef * cos_in) * scale;
 }
+/* ct_conductor_bdsf without its Fresnel factor (bdsf.c:174-186): ggx_att(out, n, m, rough) / (4 on_dot) with m = normalise(out + in),
+ * D of bdsf.c:3-20 and G1(out) of :22-42, and the micro-normal cosine |n.m| the Fresnel factor is evaluated at.  One out-of-line copy
+ * serves the next-event and the sampled-direction evaluation of the classed kernel. */
+template <typename R>
+static __device__ __noinline__ float2 ct_weight(const GeomT<R> &g, int m, V3<R> nrm, V3<R> out, R on_dot, V3<R> in)
+{
+    V3<R> mn = normalise(out + in);
+    R d = dot(nrm, mn), gg = R(0);
+    R rough = g.rough[m], r2 = rough * rough;
+    if(d > R(0))
+    {
+        R d2 = d * d, d4 = d2 * d2, tan_sq = r_div(R(1), d2) - R(1);
+        gg = r_div(r2, Num<R>::pi() * d4 * (r2 + tan_sq) * (r2 + tan_sq));
+    }
+    R v_mn = dot(out, mn), v_sn = dot(out, nrm);
+    R quot = r_abs(r_div(v_mn, v_sn)), att = R(0);
+    if(!(quot <= R(0)))
+    {
+        R tan_sq = r_div(R(1), v_sn * v_sn) - R(1);
+        att = r_div(R(2), R(1) + r_sqrt(R(1) + r2 * tan_sq));
+    }
+    return make_float2((float)((gg * att) * r_div(R(1), R(4) * on_dot)) * g.ct_mult[m], (float)r_abs(d));
+}
+
 /* dielectric Fresnel at one wavelength, bdsf.c:44-66 (Q9 kept) */
 template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr, T inc_cos)
 {
@@ -766,7 +790,11 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                 {
                     /* rough conductor: w k and the micro-normal cosine; a specular material contributes nothing to next-event
                      * estimation (its lobes are gated on the exact reflection / refraction direction, Q8) */
-                    if(cls == DRT_CLASS_ROUGH) eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, (float)k, recw, 0);
+                    if(cls == DRT_CLASS_ROUGH)
+                    {
+                        const float2 wc = ct_weight<R>(g, sm, h.nrm, h.out, h.on_dot, ldir);
+                        recw[0] = wc.x * (float)k; recw[1] = wc.y;
+                    }
                 }
                 else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, 1.f, rec, e);
                 if(!fast) rec[e + ew] = (float)k;
@@ -795,16 +823,16 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                 const uint32_t inside = (h.inc_mat != g.base_mat) ? 1u : 0u;
                 if(cls == DRT_CLASS_ROUGH)
                 {
-                    eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, recw, 2);
+                    const float2 wc = ct_weight<R>(g, sm, h.nrm, h.out, h.on_dot, in);
+                    recw[2] = wc.x * (float)inv_pdf; recw[3] = wc.y;
                     hdr16 = (uint32_t)DRT_CLASS_ROUGH | (inside << 4) | ((uint32_t)sm << 5);
                 }
                 else
                 {
-                    /* c0 + c1 X over the material's one spectral basis X: the evaluator stores the weights its lobe list can
-                     * produce in basis order, the constant (of fs_dielectric_transmittance's 1 - R) first */
-                    const int mask = g.bmask[sm];
-                    eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, recw, 0);
-                    if(!(mask & (1 << BK_CONST))) { recw[1] = recw[0]; recw[0] = 0.f; }
+                    /* (c0 + c1 X) / pdf over the material's one spectral basis X, constants tabulated per match (GeomT::spec_c) */
+                    const int mask = g.bmask[sm], mt = match & 3;
+                    recw[0] = g.spec_c[sm][mt < 3 ? mt : 0][0] * (float)inv_pdf;
+                    recw[1] = g.spec_c[sm][mt < 3 ? mt : 0][1] * (float)inv_pdf;
                     recw[2] = (float)h.on_dot;
                     const uint32_t basis = (mask & (1 << BK_MIRROR)) ? 0u : (mask & (1 << BK_DIEL_R)) ? 1u : 2u;
                     hdr16 = (uint32_t)DRT_CLASS_SPECULAR | (basis << 2) | (inside << 4) | ((uint32_t)sm << 5);
@@ -994,7 +1022,7 @@ static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *
  * Fresnel terms on the rows precomputed at upload (SpdIndex::fres): the same formulas as fresnel_dielectric / fresnel_conductor
  * above with the per-wavelength ratios taken out (rel = ir / tr;  A = eta^2 - kappa^2, B = 4 eta^2 kappa^2 with eta = tr / ir,
  * kappa = te / ir), dividing numerator and denominator of the dielectric amplitudes by tr (bdsf.c:44-101, Q9 kept). */
-__device__ __forceinline__ float fresnel_dielectric_rel(float rel, float inc_cos)
+static __device__ __noinline__ float fresnel_dielectric_rel(float rel, float inc_cos)
 {
     const float inc_sin_sq = 1.f - inc_cos * inc_cos;
     const float ts_sin_sq = rel * rel * inc_sin_sq;
@@ -1005,7 +1033,7 @@ __device__ __forceinline__ float fresnel_dielectric_rel(float rel, float inc_cos
     const float per = r_div(b - ts_cos, b + ts_cos);
     return 0.5f * (par * par + per * per);
 }
-__device__ __forceinline__ float fresnel_conductor_ab(float A, float B, float inc_cos)
+static __device__ __noinline__ float fresnel_conductor_ab(float A, float B, float inc_cos)
 {
     const float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
     const float r = A - sin_sq;
