@@ -653,7 +653,7 @@ static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int
     *warps_out = warps; *smem_out = smem;
     if(smem > ctx->smem_optin) return false;
     int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    int by_threads = (DRT_MIN_CTAS * full_warps) / warps;
+    int by_threads = (drt_render_min_ctas(ctx->f64_geometry, kernel_mode(ctx)) * full_warps) / warps;
     if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if(ctas_per_sm < 1) ctas_per_sm = 1;
     *ctas_out = ctas_per_sm;

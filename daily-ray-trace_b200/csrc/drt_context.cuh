@@ -12,6 +12,7 @@
 
 cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int mode, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
 int         drt_render_cta_warps(bool f64_geometry, int mode);
+int         drt_render_min_ctas(bool f64_geometry, int mode);
 size_t      drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots);
 void        drt_launch_film_to_rgb(const void *tables, const float *plane, const float *filter, int normalise_by_max, uint32_t npix,
                                    float *rgb, uint32_t *bgra, int grid, cudaStream_t stream);

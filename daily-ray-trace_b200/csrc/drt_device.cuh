@@ -23,7 +23,19 @@
 #define DRT_FAST_WARPS 14     /* warps per CTA of the ALLFAST kernel: 2 CTAs x 14 warps x 72 registers per SM (measured: 8 warps 6.7, 12: 9.70, 14: 9.79, 16: 9.65 G paths/s) */
 #endif
 #ifndef DRT_CLASSED_WARPS
-#define DRT_CLASSED_WARPS 12   /* warps per CTA of the classed kernel */
+#define DRT_CLASSED_WARPS 16   /* warps per CTA of the classed kernel: 2 CTAs x 16 warps x 64 registers (measured on cornell_plane_light, G paths/s at
+                                * 64 spp: 10 warps 3.96, 12: 4.09, 14: 4.34, 16: 4.53; with the phase gates 16 x 2: 5.04, 32 x 1: 4.97, 28 x 1: 4.79) */
+#endif
+#ifndef DRT_CLASSED_CTAS
+#define DRT_CLASSED_CTAS 2     /* resident CTAs per SM the classed / the general kernel is compiled for */
+#endif
+#ifndef DRT_GENERAL_CTAS
+#define DRT_GENERAL_CTAS 2
+#endif
+#ifndef DRT_LOCKSTEP
+#define DRT_LOCKSTEP 2         /* bit mask of kernel modes whose CTAs run their phases in lockstep (drt_render.cuh): bit 1 = the classed kernel
+                                * (measured +15 %: its hot code is 38 KB against a 32 KB instruction cache); bit 0 = the general kernel
+                                * (measured -26 % on stress_all: its phase-2 times differ too much between warps) */
 #endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS

@@ -26,6 +26,12 @@ int drt_render_cta_warps(bool f64_geometry, int mode)
     return mode == 1 ? DRT_FAST_WARPS : mode == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS;
 }
 
+int drt_render_min_ctas(bool f64_geometry, int mode)
+{
+    if(f64_geometry) return DRT_GENERAL_CTAS;
+    return mode == 1 ? DRT_MIN_CTAS : mode == 2 ? DRT_CLASSED_CTAS : DRT_GENERAL_CTAS;
+}
+
 size_t drt_render_smem_bytes(const RenderLaunch &L, bool f64_geometry, int warps, int nslots)
 {
     size_t geom = f64_geometry ? sizeof(GeomT<double>) : sizeof(GeomT<float>);

@@ -533,7 +533,7 @@ template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /
 /* match: bit0 = `in` came out of the reflection formula, bit1 = out of the refraction formula (Q8) */
 template <typename R> struct DirSample { V3<R> in; R inv_pdf; int match; Rng rng; };
 
-/* All six samplers, out of line and by value (the cosine-weighted one is also inlined in sample_direction below). */
+/* Five of the six samplers, out of line and by value (the cosine-weighted one is inlined in sample_direction below). */
 template <typename R>
 static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT<R> &g, Hit<R> h, Rng rng)
 {
@@ -555,19 +555,7 @@ static __device__ __noinline__ DirSample<R> sample_direction_general(const GeomT
             inv_pdf = R(2) * Num<R>::pi();
             break;
         }
-        case DRT_DIR_COS_WEIGHTED_HEMISPHERE:   /* :200-213 */
-        {
-            V3<R> q;
-            for(;;)
-            {
-                q = sample_disc<R>(rng);
-                if(dot(q, q) < R(1)) break;   /* Q16 */
-            }
-            q.z = r_sqrt(R(1) - dot(q, q));
-            in = rotate_from_z<R>(h.nrm, q);
-            inv_pdf = r_div(Num<R>::pi(), dot(h.nrm, in));
-            break;
-        }
+        /* DRT_DIR_COS_WEIGHTED_HEMISPHERE (:200-213) is handled inline by sample_direction below and never reaches this function */
         case DRT_DIR_SPECULAR:   /* :215-220 */
             in = reflect<R>(neg(h.out), h.nrm);
             inv_pdf = R(1);
@@ -1373,9 +1361,17 @@ static __device__ __noinline__ void dump_path(float *record_dump, float *path_du
 #endif
 /* PAIRED: one pixel per task with all its samples (spp >= 32) against 32/spp whole pixels per task; see the task loop. */
 template <typename R, int NS, int MODE, bool PAIRED>
-__global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS) * DRT_WARP, DRT_MIN_CTAS) render_kernel(const RenderLaunch L)
+__global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS) * DRT_WARP,
+                                   MODE == 1 ? DRT_MIN_CTAS : MODE == 2 ? DRT_CLASSED_CTAS : DRT_GENERAL_CTAS) render_kernel(const RenderLaunch L)
 {
     constexpr bool ALLFAST = MODE != 0;   /* compact records, film parked in shared memory while tracing */
+    /* LOCKSTEP (a kernel whose hot code does not fit the 32 KB instruction cache; DRT_LOCKSTEP says which modes): the warps of a CTA
+     * run their phases together -- a gate (an mbarrier that every warp arrives at once per phase and leaves for good when it runs
+     * out of pixels) in front of phase 1 and of phase 2 -- so that at any time the SM fetches the code of ONE phase. */
+    constexpr bool LOCKSTEP = MODE == 2 ? ((DRT_LOCKSTEP & 2) != 0) : MODE == 0 ? ((DRT_LOCKSTEP & 1) != 0) : false;
+    __shared__ unsigned long long phase_bar;
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&phase_bar);
+    if(LOCKSTEP && threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(blockDim.x >> 5) : "memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
     size_t off = (sizeof(GeomT<R>) + 15) & ~size_t(15);
@@ -1439,12 +1435,31 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
 
     uint32_t tally[4] = { 0u, 0u, 0u, 0u };   /* closest rays, shadow rays, shaded bounces, rng draws of this lane */
     uint32_t traced = 0;
+    uint32_t gate_parity = 0;
+    auto gate = [&]()
+    {
+        if constexpr(LOCKSTEP)
+        {
+            if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
+            __syncwarp();
+            uint32_t ok = 0;
+            while(!ok)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(bar_addr), "r"(gate_parity) : "memory");
+            gate_parity ^= 1u;
+        }
+    };
     for(;;)
     {
         uint32_t task = 0;
         if(lane == 0) task = atomicAdd(L.task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
-        if(task >= ntasks) break;
+        if(task >= ntasks)
+        {
+            /* out of pixels: this warp leaves the gates for good (it is in front of a phase-1 gate, like every warp that still works) */
+            if(LOCKSTEP && lane == 0) asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
+            break;
+        }
         task += L.task_rotate;
         if(task >= ntasks) task -= ntasks;
         const uint32_t p_begin = task * L.pixels_per_task;
@@ -1474,6 +1489,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
         for(uint32_t q0 = 0; q0 < total; q0 += DRT_WARP)
         {
             /* ---- phase 1: lane = path ---- */
+            gate();
             if((ALLFAST || DRT_PARK_GENERAL) && paired) film.park(park);
             const uint32_t q = q0 + lane;
             uint32_t bin = 9, general = 0;
@@ -1498,6 +1514,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
                 }
             }
             __syncwarp();
+            gate();
             if((ALLFAST || DRT_PARK_GENERAL) && paired) film.unpark(park);
             {
                 /* termination histogram: one shared-memory atomic per distinct bin of the batch (bin 9 = idle lane) */
