@@ -493,27 +493,6 @@ template <typename T> __device__ __forceinline__ T fresnel_dielectric(T ir, T tr
     return T(0.5) * (par * par + per * per);
 }
 
-/* conductor Fresnel at one wavelength, bdsf.c:78-101 */
-__device__ __forceinline__ float fresnel_conductor(float ir, float tr, float te, float inc_cos)
-{
-    float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
-    float inv_ir = r_rcp_fast(ir);
-    float eta = tr * inv_ir, kap = te * inv_ir;
-    float eta_sq = eta * eta, kap_sq = kap * kap;
-    float r = eta_sq - kap_sq - sin_sq;
-    float apb_sq = r_sqrt_fast(r * r + 4.f * eta_sq * kap_sq);
-    /* with kappa = 0 this is sqrt(|r| + r): exactly 0 for r < 0 in IEEE arithmetic (sqrt(r*r) == |r|), but the approximate
-     * square root of the fast-math build may land one ulp low -> clamp instead of producing a NaN wavelength */
-    float a = r_sqrt_fast(fmaxf(0.5f * (apb_sq + r), 0.f));
-    float s = apb_sq + cos_sq;
-    float t = 2.f * a * inc_cos;
-    float u = cos_sq * apb_sq + sin_sq * sin_sq;
-    float v = t * sin_sq;
-    float par = r_div(s - t, s + t);
-    float per = r_div(par * (u - v), u + v);
-    return 0.5f * (par + per);
-}
-
 /* ------------------------------------------------------------------ K4: the six direction samplers, bdsf.c:191-292 */
 
 template <typename R> __device__ __forceinline__ V3<R> sample_disc(Rng &rng)   /* uniform_sample_disc, rng.c:25-51 */
@@ -923,93 +902,11 @@ template <int NS> __device__ __forceinline__ void v_sub(float (&o)[NS], const fl
 template <int NS> struct Spec { float v[NS]; };
 template <int NS> struct ShadeState { Spec<NS> thr, dst; };
 
-/* All seven spectral bases at ONE wavelength (table values d, g, m; refraction/extinction ir, tr, te).  Out of line and
- * scalar, so the Fresnel formulas exist once in the kernel however many wavelength slots a lane holds: this code is cold
- * for the shipped walls but must stay small enough not to evict the hot path from the instruction cache. */
-struct EvalWeights { float w_const, w_d, w_g, w_m, w_r, w_a, c_a, w_b, c_b, on_dot; };
-
-static __device__ __noinline__ float eval_general_one(EvalWeights e, float d, float g, float m, float ir, float tr, float te)
-{
-    float f = e.w_const;
-    f = fmaf(e.w_d, d, f);
-    f = fmaf(e.w_g, g, f);
-    f = fmaf(e.w_m, m, f);
-    if(e.w_r != 0.f) f = fmaf(e.w_r, fresnel_dielectric<float>(ir, tr, e.on_dot), f);
-#pragma unroll 1
-    for(int t = 0; t < 2; t += 1)   /* F(on_dot) of fs_conductor_bdsf, F(mn_dot) of ct_conductor_bdsf: one loop body */
-    {
-        float w = t ? e.w_b : e.w_a, cs = t ? e.c_b : e.c_a;
-        if(w != 0.f) f = fmaf(w, fresnel_conductor(ir, tr, te, cs), f);
-    }
-    return f;
-}
-
-/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list.  `mask` is warp-uniform. */
-template <int NS>
-__device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
-                                                          int surf_mat, int inc_mat, int trans_mat, float on_dot)
-{
-    EvalWeights e;
-    e.w_const = e.w_d = e.w_g = e.w_m = e.w_r = e.w_a = e.c_a = e.w_b = e.c_b = 0.f;
-    e.on_dot = on_dot;
-    if(mask & (1 << BK_CONST))   { e.w_const = col[at]; at += 1; }
-    if(mask & (1 << BK_DIFFUSE)) { e.w_d = col[at]; at += 1; }
-    if(mask & (1 << BK_GLOSSY))  { e.w_g = col[at]; at += 1; }
-    if(mask & (1 << BK_MIRROR))  { e.w_m = col[at]; at += 1; }
-    if(mask & (1 << BK_DIEL_R))  { e.w_r = col[at]; at += 1; }
-    if(mask & (1 << BK_COND_ON)) { e.w_a = col[at]; e.c_a = on_dot; at += 1; }
-    if(mask & (1 << BK_COND_MN)) { e.w_b = col[at]; e.c_b = col[at + 1]; }
-    const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];     /* absent spectra point at the all-zero row */
-    const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
-    const float *mr = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
-    const float *ir = pool_lane + ix.row[inc_mat][DRT_SPD_REFRACT];
-    const float *tr = pool_lane + ix.row[trans_mat][DRT_SPD_REFRACT];
-    const float *te = pool_lane + ix.row[trans_mat][DRT_SPD_EXTINCT];
-    Spec<NS> f;
-#pragma unroll
-    for(int k = 0; k < NS; k += 1)
-        f.v[k] = eval_general_one(e, dr[k * DRT_HALF], gr[k * DRT_HALF], mr[k * DRT_HALF], ir[k * DRT_HALF], tr[k * DRT_HALF], te[k * DRT_HALF]);
-    return f;
-}
-
-/* One shaded bounce of cast_ray (daily_ray_trace.c:458-473) for any material and any number of lights, out of line. */
-template <int NS, typename G>
-static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, uint32_t base, uint32_t hdr, const G &g, const SpdIndex &ix,
-                                                            const float *pool_lane, uint32_t ew, int nlights, ShadeState<NS> st)
-{
-    const int surf_mat = (hdr >> 3) & 31;
-    const int mask = g.bmask[surf_mat];
-    const bool swapped = (hdr >> 8) & 1u;
-    const int inc_mat = swapped ? surf_mat : g.base_mat, trans_mat = swapped ? g.base_mat : surf_mat;
-    const uint32_t vis = hdr >> 16;
-    const float on_dot = col[base + 1];
-    float contrib[NS];
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) contrib[k] = 0.f;
-#pragma unroll 1
-    for(int j = 0; j < nlights; j += 1)
-    {
-        if(!((vis >> j) & 1u)) continue;
-        uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
-        Spec<NS> f = eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot);
-        float kk = col[e + ew];
-        const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
-#pragma unroll
-        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_HALF]) * kk;   /* Q4 */
-    }
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], contrib[k], st.dst.v[k]);
-    Spec<NS> f = eval_spectrum_general<NS>(col, base + 2 + (ew + 1) * (uint32_t)nlights, mask, ix, pool_lane, surf_mat, inc_mat, trans_mat, on_dot);
-#pragma unroll
-    for(int k = 0; k < NS; k += 1) st.thr.v[k] *= f.v[k];
-    return st;
-}
-
-/* ------------------------------------------------------------------ classed kernel: specular and rough-conductor bounces
- *
- * Fresnel terms on the rows precomputed at upload (SpdIndex::fres): the same formulas as fresnel_dielectric / fresnel_conductor
- * above with the per-wavelength ratios taken out (rel = ir / tr;  A = eta^2 - kappa^2, B = 4 eta^2 kappa^2 with eta = tr / ir,
- * kappa = te / ir), dividing numerator and denominator of the dielectric amplitudes by tr (bdsf.c:44-101, Q9 kept). */
+/* Fresnel terms on the rows precomputed at upload (SpdIndex::fres): the formulas of fresnel_dielectric above and of
+ * fs_conductor_reflectance (bdsf.c:78-101) with the per-wavelength ratios taken out (rel = ir / tr;  A = eta^2 - kappa^2,
+ * B = 4 eta^2 kappa^2 with eta = tr / ir, kappa = te / ir), numerator and denominator of the dielectric amplitudes divided by tr
+ * (bdsf.c:44-76, Q9 kept).  Scalar and out of line: each formula exists once in a kernel however many wavelength slots a lane holds
+ * -- the kernels that contain them are bound by instruction fetch, so small code beats straight-line code. */
 static __device__ __noinline__ float fresnel_dielectric_rel(float rel, float inc_cos)
 {
     const float inc_sin_sq = 1.f - inc_cos * inc_cos;
@@ -1036,6 +933,83 @@ static __device__ __noinline__ float fresnel_conductor_ab(float A, float B, floa
     return 0.5f * (par + per);
 }
 
+/* One BSDF evaluation expanded over this lane's wavelengths, any lobe list: the stored weights of the seven spectral bases
+ * (eval_weights_general) times the bases.  `mask` is warp-uniform; a Fresnel basis whose weight is zero (every match-gated lobe under
+ * next-event estimation) is not evaluated. */
+template <int NS>
+__device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint32_t at, int mask, const SpdIndex &ix, const float *pool_lane,
+                                                          int surf_mat, int inside, float on_dot)
+{
+    float w_const = 0.f, w_d = 0.f, w_g = 0.f, w_m = 0.f, w_r = 0.f, w_a = 0.f, w_b = 0.f, c_b = 0.f;
+    if(mask & (1 << BK_CONST))   { w_const = col[at]; at += 1; }
+    if(mask & (1 << BK_DIFFUSE)) { w_d = col[at]; at += 1; }
+    if(mask & (1 << BK_GLOSSY))  { w_g = col[at]; at += 1; }
+    if(mask & (1 << BK_MIRROR))  { w_m = col[at]; at += 1; }
+    if(mask & (1 << BK_DIEL_R))  { w_r = col[at]; at += 1; }
+    if(mask & (1 << BK_COND_ON)) { w_a = col[at]; at += 1; }
+    if(mask & (1 << BK_COND_MN)) { w_b = col[at]; c_b = col[at + 1]; }
+    const float *dr = pool_lane + ix.row[surf_mat][DRT_SPD_DIFFUSE];     /* absent spectra point at the all-zero row */
+    const float *gr = pool_lane + ix.row[surf_mat][DRT_SPD_GLOSSY];
+    const float *mr = pool_lane + ix.row[surf_mat][DRT_SPD_MIRROR];
+    Spec<NS> f;
+#pragma unroll
+    for(int k = 0; k < NS; k += 1)
+        f.v[k] = fmaf(w_m, mr[k * DRT_HALF], fmaf(w_g, gr[k * DRT_HALF], fmaf(w_d, dr[k * DRT_HALF], w_const)));
+    if(w_r != 0.f)
+    {
+        const float *rel = pool_lane + ix.fres[surf_mat][inside][0];
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w_r, fresnel_dielectric_rel(rel[k * DRT_HALF], on_dot), f.v[k]);
+    }
+    if(w_a != 0.f || w_b != 0.f)
+    {
+        const float *ra = pool_lane + ix.fres[surf_mat][inside][1], *rb = pool_lane + ix.fres[surf_mat][inside][2];
+#pragma unroll 1
+        for(int t = 0; t < 2; t += 1)   /* F(on_dot) of fs_conductor_bdsf, F(micro-normal cosine) of ct_conductor_bdsf: one loop body */
+        {
+            const float w = t ? w_b : w_a, cs = t ? c_b : on_dot;
+            if(w == 0.f) continue;
+#pragma unroll
+            for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], cs), f.v[k]);
+        }
+    }
+    return f;
+}
+
+/* One shaded bounce of cast_ray (daily_ray_trace.c:458-473) for any material and any number of lights, out of line. */
+template <int NS, typename G>
+static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *col, uint32_t base, uint32_t hdr, const G &g, const SpdIndex &ix,
+                                                            const float *pool_lane, uint32_t ew, int nlights, ShadeState<NS> st)
+{
+    const int surf_mat = (hdr >> 3) & 31;
+    const int mask = g.bmask[surf_mat];
+    const bool swapped = (hdr >> 8) & 1u;
+    const int inside = swapped ? 1 : 0;   /* the orientation of the Fresnel rows: 1 = incident medium is the surface's material (Q11) */
+    const uint32_t vis = hdr >> 16;
+    const float on_dot = col[base + 1];
+    float contrib[NS];
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) contrib[k] = 0.f;
+#pragma unroll 1
+    for(int j = 0; j < nlights; j += 1)
+    {
+        if(!((vis >> j) & 1u)) continue;
+        uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+        Spec<NS> f = eval_spectrum_general<NS>(col, e, mask, ix, pool_lane, surf_mat, inside, on_dot);
+        float kk = col[e + ew];
+        const float *erow = pool_lane + ix.row[g.mat[g.light_surf[j]]][DRT_SPD_EMISSION];
+#pragma unroll
+        for(int k = 0; k < NS; k += 1) contrib[k] = ((contrib[k] + f.v[k]) * erow[k * DRT_HALF]) * kk;   /* Q4 */
+    }
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) st.dst.v[k] = fmaf(st.thr.v[k], contrib[k], st.dst.v[k]);
+    Spec<NS> f = eval_spectrum_general<NS>(col, base + 2 + (ew + 1) * (uint32_t)nlights, mask, ix, pool_lane, surf_mat, inside, on_dot);
+#pragma unroll
+    for(int k = 0; k < NS; k += 1) st.thr.v[k] *= f.v[k];
+    return st;
+}
+
+/* ------------------------------------------------------------------ classed kernel: specular and rough-conductor bounces */
 /* u = throughput * E and the radiance of a path, as the replay loop of the compact-record kernels carries them */
 template <int NS> struct Carry { float u[NS], d[NS]; };
 
