@@ -274,6 +274,25 @@ def algorithmic_flops_per_path(scene, st, n):
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this rank's host thread to the CPUs NVML reports as local to its GPU, so that the pages of the host film it first
+    touches (its own slice) sit on the memory controllers next to its PCIe link.  Returns the number of CPUs, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class SharedHostFilm:
     """One page-locked host film that every rank of the node writes its own slice into (POSIX shared memory mapped and
     cudaHostRegister-ed by every process): the host-side destination of the per-rank read-back.  Plumbing only."""
@@ -315,6 +334,15 @@ class SharedHostFilm:
                 else:
                     merged.append((lo, hi))
             ranges = merged
+        # first touch by the rank that will DMA into the pages (NUMA placement; see pin_to_gpu_numa_node)
+        if pixel_range is not None:
+            for plane, width in ((0, n), (1, n), (2, n)):
+                flat[plane * npix * n + p0 * width:plane * npix * n + p1 * width] = 0.0
+            flat[3 * npix * n + p0:3 * npix * n + p1] = 0.0
+        else:
+            flat[:] = 0.0
+        if world > 1:
+            dist.barrier()
         self.registered = []
         for lo, hi in ranges:
             rc = torch.cuda.cudart().cudaHostRegister(base + lo, hi - lo, 0)
@@ -358,6 +386,7 @@ def run_b200_arm(a):
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -479,14 +508,28 @@ def run_b200_arm(a):
     host_film = host.drt_film(cuda) if host is not None else None
     d2h = [0]
 
+    e2e_marks = None
+
+    copy_stream = torch.cuda.Stream() if group is not None else None
+
+    def mark_e2e(name, on=None):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(on or stream)
+        e2e_marks[name] = ev
+
     def e2e_step():
         ctx.upload_scene(scene, camera, tables)
+        if e2e_marks is not None:
+            mark_e2e("uploaded")
         if world == 1:
             ctx.render_host_into(prm, host_film)
             d2h[0] = (3 * npix * n + npix) * 4
         elif group is not None:
-            step()
-            d2h[0] = group.read_back(host_film, stream.cuda_stream)
+            _, d2h[0] = group.step_bands_to_host(prm, host_film, stream.cuda_stream, copy_stream.cuda_stream)
+            if e2e_marks is not None:
+                mark_e2e("rendered")
+                mark_e2e("on_host", copy_stream)
+            copy_stream.synchronize()
             stream.synchronize()
         else:
             step()
@@ -510,6 +553,18 @@ def run_b200_arm(a):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         dist.all_reduce(d2h_all, op=dist.ReduceOp.SUM)
     e2e_s = float(e2e_s.item())
+    e2e_phases = None
+    if group is not None:       # one more step with events between its phases (device times; max over ranks)
+        e2e_marks = {}
+        e2e_step()
+        fence()
+        mine = torch.tensor([e2e_marks["uploaded"].elapsed_time(e2e_marks["rendered"]), e2e_marks["uploaded"].elapsed_time(e2e_marks["on_host"])], device="cuda")
+        e2e_marks = None
+        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+        e2e_phases = {"render_stream_ms": float(mine[0]), "until_slice_on_host_ms": float(mine[1]), "bands": len(group.BAND_CUTS) - 1,
+                      "host_threads_numa_bound_cpus": numa,
+                      "note": "the frame is rendered in bands (the same part of every owner's slice per band); owners merge and read back band b "
+                              "on a second stream while band b + 1 renders"}
     upload_bytes = ctx.scene_upload_bytes() * world
     d2h_bytes = int(d2h_all.item())
     if group is not None:
@@ -554,9 +609,9 @@ def run_b200_arm(a):
             "paths_traced_fraction": traced_fraction,
             "clocks": clocks,
             "e2e": {"value": paths_per_step * a.steps / e2e_s, "unit": "paths/s", "h2d_bytes_per_step": upload_bytes,
-                    "d2h_bytes_per_step": d2h_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "phases": e2e_phases,
                     "note": "scene upload + render (+ exchange) + film read-back into page-locked host memory, wall clock, max over ranks"
-                            + ("; every rank reads its own merged slice back over its own PCIe link into one shared host film" if group is not None else "")},
+                            + ("; every rank reads its own merged slice back over its own PCIe link into one shared host film, band by band under the render" if group is not None else "")},
             "gpu_launches": launches_step * a.steps,
             "film_exchange_ms": exchange_ms,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

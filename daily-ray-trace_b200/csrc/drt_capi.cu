@@ -682,7 +682,8 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_rend
 
 static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
                   FilmPtrs film, float *dump, int accumulate, cudaStream_t stream, float *record_dump = nullptr, uint32_t *path_words_out = nullptr,
-                  const drt_film *scatter = nullptr, int scatter_count = 0, int scatter_rank = 0, uint64_t scatter_slice = 0, bool keep_stats = false)
+                  const drt_film *scatter = nullptr, int scatter_count = 0, int scatter_rank = 0, uint64_t scatter_slice = 0, bool keep_stats = false,
+                  uint64_t band_begin = 0, uint64_t band_end = 0)
 {
     if(!ctx->have_scene) return fail(DRT_CUDA_E_STATE, "upload a scene first");
     if(p->width == 0 || p->height == 0 || x1 > p->width || y1 > p->height || x0 >= x1 || y0 >= y1) return fail(DRT_CUDA_E_ARG, "bad image rectangle");
@@ -732,8 +733,17 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
         return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
                     p->max_depth, ctx->nlights, smem, ctx->smem_optin);
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
-    uint64_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
-    if(scatter_count > 1) L.task_rotate = (uint32_t)((((uint64_t)scatter_rank * scatter_slice) / L.pixels_per_task) % ntasks);
+    const bool band = band_end > band_begin;
+    if(band)
+    {
+        if(L.pixels_per_task != 1 || scatter_count < 1 || band_end > scatter_slice || x0 != 0 || y0 != 0 || x1 != p->width || y1 != p->height)
+            return fail(DRT_CUDA_E_ARG, "a band needs a scattered whole-frame render with at least 32 samples per pixel");
+        L.band_chunk = (uint32_t)(band_end - band_begin); L.band_period = (uint32_t)scatter_slice; L.band_base = (uint32_t)band_begin;
+    }
+    uint64_t ntasks = band ? (uint64_t)L.band_chunk * scatter_count : (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+    if(scatter_count > 1)
+        L.task_rotate = band ? (uint32_t)(((uint64_t)scatter_rank * L.band_chunk) % ntasks)
+                             : (uint32_t)((((uint64_t)scatter_rank * scatter_slice) / L.pixels_per_task) % ntasks);
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
     uint64_t need = (ntasks + warps - 1) / warps;
     if(grid > need) grid = need;
@@ -769,6 +779,20 @@ extern "C" int drt_cuda_render_device_scatter(drt_cuda_context *ctx, const drt_r
         if(!staging[i].sum || !staging[i].filter || !staging[i].mean || !staging[i].m2) return fail(DRT_CUDA_E_ARG, "NULL staging film %d", i);
     FilmPtrs f = { staging[0].sum, staging[0].filter, staging[0].mean, staging[0].m2 };
     return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, (cudaStream_t)stream, nullptr, nullptr, staging, count, rank, slice_pixels);
+}
+
+extern "C" int drt_cuda_render_device_scatter_band(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *staging, int count, int rank,
+                                                   uint64_t slice_pixels, uint64_t band_begin, uint64_t band_end, int keep_stats, void *stream)
+{
+    if(!ctx || !params || !staging || count < 1 || count > DRT_MAX_PEERS || rank < 0 || rank >= count) return fail(DRT_CUDA_E_ARG, "bad argument (1..%d staging films)", DRT_MAX_PEERS);
+    uint64_t npix = (uint64_t)params->width * params->height;
+    if(slice_pixels == 0 || slice_pixels * (uint64_t)count < npix || slice_pixels > 0xffffffffull) return fail(DRT_CUDA_E_ARG, "slices of %llu pixels do not cover the image", (unsigned long long)slice_pixels);
+    if(band_begin >= band_end || band_end > slice_pixels) return fail(DRT_CUDA_E_ARG, "bad band [%llu, %llu) of a slice of %llu pixels", (unsigned long long)band_begin, (unsigned long long)band_end, (unsigned long long)slice_pixels);
+    for(int i = 0; i < count; i += 1)
+        if(!staging[i].sum || !staging[i].filter || !staging[i].mean || !staging[i].m2) return fail(DRT_CUDA_E_ARG, "NULL staging film %d", i);
+    FilmPtrs f = { staging[0].sum, staging[0].filter, staging[0].mean, staging[0].m2 };
+    return launch(ctx, params, 0, 0, params->width, params->height, f, nullptr, 0, (cudaStream_t)stream, nullptr, nullptr, staging, count, rank, slice_pixels,
+                  keep_stats != 0, band_begin, band_end);
 }
 
 int drt_ensure_buffer(float **buf, size_t *have, size_t need)

@@ -204,6 +204,11 @@ struct RenderLaunch
      * (cast_ray :451-452), so they are counted, not traced.  The full image when no bound is known. */
     uint32_t hit_x0, hit_y0, hit_x1, hit_y1;
     uint32_t scatter_count, scatter_rank, scatter_slice;
+    /* Band of a scattered render (drt_cuda_render_device_scatter_band): the launch covers, for every owner o, the pixels
+     * [o * band_period + band_base, + band_chunk) -- the same part of every owner's slice -- so that the owners can merge and read
+     * back band b while band b + 1 renders.  Task t is pixel (t / band_chunk) * band_period + band_base + t % band_chunk (tasks past
+     * the end of the image are empty).  band_chunk = 0: the plain row-major walk of the rectangle. */
+    uint32_t band_chunk, band_period, band_base;
     uint32_t task_rotate;          /* tasks are walked from this index (mod the task count): with scatter_rank * slice every rank starts in its own
                                     * slice, so at any moment each owner receives from one peer instead of from all of them */
     FilmPtrs scatter[DRT_MAX_PEERS];

@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
     const uint32_t n = (uint32_t)ix.n;
-    const uint32_t ntasks = (npix + L.pixels_per_task - 1) / L.pixels_per_task;
+    const uint32_t ntasks = (PAIRED && L.band_chunk) ? L.band_chunk * L.scatter_count : (npix + L.pixels_per_task - 1) / L.pixels_per_task;
     const bool have_film = L.film.sum != nullptr;
     /* A task is one pixel with all its samples (spp >= 32: `paired`, the film stays in registers across the pixel's batches of
      * 32 paths) or 32/spp whole pixels traced as ONE batch.  Either way phase 2 walks the batch pixel by pixel, both half
@@ -1436,8 +1436,13 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
         }
         task += L.task_rotate;
         if(task >= ntasks) task -= ntasks;
-        const uint32_t p_begin = task * L.pixels_per_task;
-        const uint32_t p_end = min(p_begin + L.pixels_per_task, npix);
+        uint32_t p_begin = task * L.pixels_per_task;
+        if(paired && L.band_chunk)   /* a band of a scattered render: the same part of every owner's slice */
+        {
+            p_begin = (p_begin / L.band_chunk) * L.band_period + L.band_base + p_begin % L.band_chunk;
+            if(p_begin >= L.width * L.height) continue;
+        }
+        const uint32_t p_end = paired ? p_begin + 1u : min(p_begin + L.pixels_per_task, npix);
         const uint32_t total = (p_end - p_begin) * spp;
         traced += total;
 

@@ -19,7 +19,7 @@ EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "d
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
            "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close",
            "drt_cuda_film_merge_slices_local", "drt_cuda_film_read_slice", "drt_cuda_flags_signal", "drt_cuda_flags_wait", "drt_cuda_flags_timeouts",
-           "drt_cuda_host_alloc", "drt_cuda_host_free"]
+           "drt_cuda_host_alloc", "drt_cuda_host_free", "drt_cuda_render_host_multi_images", "drt_cuda_render_device_scatter_band"]
 
 
 class Film(C.Structure):
@@ -73,7 +73,8 @@ def lib():
         L.drt_cuda_render_host.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film)]
         L.drt_cuda_film_merge_slices_local.argtypes = [C.c_void_p, C.POINTER(Film), C.POINTER(Film), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                                                        C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.drt_cuda_film_read_slice.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint64, C.c_uint64, C.POINTER(Film), C.c_void_p]
+        L.drt_cuda_film_read_slice.argtypes = [C.c_void_p, C.POINTER(Film), C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Film), C.c_void_p]
+        L.drt_cuda_render_device_scatter_band.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.POINTER(Film), C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         L.drt_cuda_flags_signal.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_void_p]
         L.drt_cuda_flags_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
         L.drt_cuda_flags_timeouts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
@@ -255,8 +256,13 @@ class Context:
         _check(lib().drt_cuda_film_merge_slices_local(self._h, C.byref(slice_film), C.byref(staging), count, slice_pixels, width, height,
                                                       pixel_begin, pixel_end, b[0], b[1], b[2], stream))
 
-    def film_read_slice(self, slice_film, pixel_begin, pixel_end, host_film, stream=None):
-        _check(lib().drt_cuda_film_read_slice(self._h, C.byref(slice_film), pixel_begin, pixel_end, C.byref(host_film), stream))
+    def film_read_slice(self, slice_film, slice_begin, pixel_begin, pixel_end, host_film, stream=None):
+        _check(lib().drt_cuda_film_read_slice(self._h, C.byref(slice_film), slice_begin, pixel_begin, pixel_end, C.byref(host_film), stream))
+
+    def render_device_scatter_band(self, params, staging, rank, slice_pixels, band_begin, band_end, keep_stats=False, stream=None):
+        arr = (Film * len(staging))(*staging)
+        _check(lib().drt_cuda_render_device_scatter_band(self._h, C.byref(params), arr, len(staging), rank, slice_pixels, band_begin, band_end,
+                                                         int(keep_stats), stream))
 
     def flags_signal(self, targets, value, stream=None):
         arr = (C.c_void_p * len(targets))(*targets)

@@ -85,7 +85,10 @@ class ShardedFilmGroup:
     buffer while slow owners may still be merging step e, and a rank can only reach step e+2 after every rank finished
     rendering e+1, i.e. after every owner finished merging e.  torch.distributed only exchanges the IPC handles at set-up."""
 
-    ARRIVE, DONE, WORDS = 0, 32, 64      # flag block: arrive[parity][rank] at parity*16 + rank, done[rank] at 32 + rank
+    ARRIVE, DONE, MERGED, WORDS = 0, 32, 48, 64   # flag block: arrive[parity][rank] at parity*16 + rank, done[rank] at 32 + rank,
+                                                  # merged[owner] at 48 + owner (banded steps: owner has merged the whole step)
+    BAND_CUTS = (0, 4, 8, 12, 14, 15, 16)         # band boundaries in 1/16 of a slice: ever smaller bands, so that the merge and
+                                                  # read-back left exposed after the last render is 1/16 of the slice
 
     def __init__(self, ctx, width, height, root=0, group=None):
         self.ctx, self.width, self.height, self.root, self.group = ctx, width, height, root, group
@@ -124,6 +127,7 @@ class ShardedFilmGroup:
             self._bufs.append(self.img_base)
         self.bgra = [self.img_base + i * npix * 4 for i in range(3)]
         self.epoch = 0
+        self.steps = 0            # banded steps issued (their parity picks the staging buffer)
         dist.barrier(group=group)
 
     def step(self, params, stream_ptr=None, mark=None):
@@ -146,9 +150,50 @@ class ShardedFilmGroup:
         if mark: mark("done")
         return 5 + (1 if self.rank == self.root else 0)      # kernels of this library launched by the step
 
+    def step_bands_to_host(self, params, host_film, render_stream_ptr, copy_stream_ptr):
+        """One render + exchange + read-back into the whole host film `host_film`, pipelined in bands: the render kernel walks the
+        same part of EVERY owner's slice per band (drt_cuda_render_device_scatter_band) on the render stream; on the copy stream
+        every owner waits for the band's arrival flags, merges the band's part of its slice and copies it to the host over its own
+        PCIe link -- while the next band renders.  Returns (kernels launched, bytes this rank copied to the host).  The caller
+        synchronises the copy stream (then the host film holds this rank's slice)."""
+        ctx = self.ctx
+        self.steps += 1
+        k, par = self.steps, self.steps & 1
+        launches = 0
+        # staging[par] was last written in banded step k - 2: every owner must have merged that step before it is overwritten
+        if k > 2:
+            ctx.flags_wait(self.flags + 4 * self.MERGED, self.world, k - 2, stream=render_stream_ptr)
+            launches += 1
+        cuts = self.BAND_CUTS if params.sample_end - params.sample_begin >= 32 and self.slice >= 64 else (0, 16)
+        copied = 0
+        first = True
+        for b in range(len(cuts) - 1):
+            b0, b1 = self.slice * cuts[b] // 16, self.slice * cuts[b + 1] // 16
+            if b1 <= b0:
+                continue
+            self.epoch += 1
+            e = self.epoch
+            if len(cuts) > 2:
+                ctx.render_device_scatter_band(params, self.peer_staging[par], self.rank, self.slice, b0, b1, keep_stats=not first, stream=render_stream_ptr)
+            else:
+                ctx.render_device_scatter(params, self.peer_staging[par], self.rank, self.slice, stream=render_stream_ptr)
+            first = False
+            ctx.flags_signal([f + 4 * (self.ARRIVE + 16 * par + self.rank) for f in self.peer_flags], e, stream=render_stream_ptr)
+            ctx.flags_wait(self.flags + 4 * (self.ARRIVE + 16 * par), self.world, e, stream=copy_stream_ptr)
+            q0, q1 = min(self.p1, self.p0 + b0), min(self.p1, self.p0 + b1)
+            launches += 3
+            if q1 > q0:
+                ctx.film_merge_slices_local(self.mine, self.staging[par], self.world, self.slice, self.width, self.height, q0, q1,
+                                            bgra=self.bgra, stream=copy_stream_ptr)
+                ctx.film_read_slice(self.mine, self.p0, q0, q1, host_film, stream=copy_stream_ptr)
+                copied += (q1 - q0) * (3 * ctx.n + 1) * 4
+                launches += 1
+        ctx.flags_signal([f + 4 * (self.MERGED + self.rank) for f in self.peer_flags], k, stream=copy_stream_ptr)
+        return launches + 1, copied
+
     def read_back(self, host_film, stream_ptr=None):
         """This rank's merged slice -> its place in a whole host film (four stream-ordered copies over this rank's PCIe link)."""
-        self.ctx.film_read_slice(self.mine, self.p0, self.p1, host_film, stream=stream_ptr)
+        self.ctx.film_read_slice(self.mine, self.p0, self.p0, self.p1, host_film, stream=stream_ptr)
         return (self.p1 - self.p0) * (3 * self.ctx.n + 1) * 4
 
     def check(self):

@@ -6,8 +6,11 @@
  * (win32_main.c:129-152).  The render itself goes through the C ABI of include/drt_cuda.h; the timed region is the
  * reference's render_timer scope (sampling + film accumulation, daily_ray_trace.c:709-752; file I/O excluded).
  *
- *   drt_raytrace [config.cfg] [--device N] [--gpus G] [--seed S] [--strict] [--f64-geometry]
- * --gpus G renders on devices N .. N+G-1: the samples of every pixel are split over them (drt_cuda_render_host_multi).
+ *   drt_raytrace [config.cfg] [--device N] [--gpus G] [--seed S] [--strict] [--f64-geometry] [--cpu-images]
+ * --gpus G renders on devices N .. N+G-1: the samples of every pixel are split over them (drt_cuda_render_host_multi_images).
+ * The three .bmp images come from the devices with the film (converted from the merged film there, fused into the multi-GPU merge
+ * kernel); --cpu-images converts them the reference's way instead: by reading the .spd files back (spd_file_to_rgb_f64_pixels,
+ * daily_ray_trace.c:1-28, in f64 -- bytes may differ by 1 from the device's f32 conversion).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,7 +42,7 @@ static int spd_to_bmp(const char *spd, const char *bmp, const drt_tables *t)
 int main(int argc, char **argv)
 {
     const char *config_path = "config.cfg";
-    int device = 0, gpus = 1, flags = DRT_PARSE_LEGACY_COMPAT, precision = DRT_GEOMETRY_F32;
+    int device = 0, gpus = 1, flags = DRT_PARSE_LEGACY_COMPAT, precision = DRT_GEOMETRY_F32, cpu_images = 0;
     unsigned long long seed = 0;
     for(int i = 1; i < argc; i += 1)
     {
@@ -48,6 +51,7 @@ int main(int argc, char **argv)
         else if(strcmp(argv[i], "--seed") == 0 && i + 1 < argc) seed = strtoull(argv[++i], NULL, 0);
         else if(strcmp(argv[i], "--strict") == 0) flags = DRT_PARSE_STRICT;
         else if(strcmp(argv[i], "--f64-geometry") == 0) precision = DRT_GEOMETRY_F64;
+        else if(strcmp(argv[i], "--cpu-images") == 0) cpu_images = 1;
         else config_path = argv[i];
     }
 
@@ -74,11 +78,19 @@ int main(int argc, char **argv)
         drt_cuda_set_geometry_precision(ctxs[g], precision);
     }
 
+    /* host film and images in page-locked memory (read-backs run as DMA, all devices at once); pageable memory if that is refused */
     size_t npix = (size_t)cfg.output_width * cfg.output_height, n = (size_t)scene.num_wavelengths;
     drt_film film;
-    film.sum = (float *)malloc(npix * n * 4); film.mean = (float *)malloc(npix * n * 4);
-    film.m2 = (float *)malloc(npix * n * 4);  film.filter = (float *)malloc(npix * 4);
-    if(!film.sum || !film.mean || !film.m2 || !film.filter) { fprintf(stderr, "ERROR: out of host memory\n"); return 1; }
+    uint32_t *images[3] = { NULL, NULL, NULL };
+    void *blocks[7] = { NULL };
+    const size_t sizes[7] = { npix * n * 4, npix * n * 4, npix * n * 4, npix * 4, npix * 4, npix * 4, npix * 4 };
+    int pinned = 1;
+    for(int i = 0; i < 7 && pinned; i += 1) if(drt_cuda_host_alloc(sizes[i] ? sizes[i] : 4, &blocks[i]) != DRT_CUDA_OK) pinned = 0;
+    if(!pinned)
+        for(int i = 0; i < 7; i += 1) { if(blocks[i]) drt_cuda_host_free(blocks[i]); blocks[i] = malloc(sizes[i] ? sizes[i] : 4); }
+    for(int i = 0; i < 7; i += 1) if(!blocks[i]) { fprintf(stderr, "ERROR: out of host memory\n"); return 1; }
+    film.sum = (float *)blocks[0]; film.mean = (float *)blocks[1]; film.m2 = (float *)blocks[2]; film.filter = (float *)blocks[3];
+    for(int i = 0; i < 3; i += 1) images[i] = (uint32_t *)blocks[4 + i];
 
     drt_render_params prm;
     memset(&prm, 0, sizeof(prm));
@@ -88,7 +100,9 @@ int main(int argc, char **argv)
 
     printf("Starting render...\n");
     double t0 = now_ms();
-    if(drt_cuda_render_host_multi(ctxs, gpus, &prm, &film) != DRT_CUDA_OK) return die_cuda("render");
+    int rrc = cpu_images ? drt_cuda_render_host_multi(ctxs, gpus, &prm, &film)
+                         : drt_cuda_render_host_multi_images(ctxs, gpus, &prm, &film, images[0], images[1], images[2]);
+    if(rrc != DRT_CUDA_OK) return die_cuda("render");
     double ms = now_ms() - t0;
     drt_cuda_stats st;
     memset(&st, 0, sizeof(st));
@@ -108,12 +122,21 @@ int main(int argc, char **argv)
     if(drt_write_spd_plain(cfg.average_spd, &tables, prm.width, prm.height, film.mean, 0) != DRT_OK) return die_host("average spd");
     if(drt_write_spd_plain(cfg.variance_spd, &tables, prm.width, prm.height, film.m2, 1) != DRT_OK) return die_host("variance spd");
     printf("Converting...\n");
-    if(spd_to_bmp(cfg.output_spd, cfg.output_bmp, &tables) != 0) return die_host("output bmp");
-    if(spd_to_bmp(cfg.average_spd, cfg.average_bmp, &tables) != 0) return die_host("average bmp");
-    if(spd_to_bmp(cfg.variance_spd, cfg.variance_bmp, &tables) != 0) return die_host("variance bmp");
+    if(cpu_images)
+    {
+        if(spd_to_bmp(cfg.output_spd, cfg.output_bmp, &tables) != 0) return die_host("output bmp");
+        if(spd_to_bmp(cfg.average_spd, cfg.average_bmp, &tables) != 0) return die_host("average bmp");
+        if(spd_to_bmp(cfg.variance_spd, cfg.variance_bmp, &tables) != 0) return die_host("variance bmp");
+    }
+    else
+    {
+        if(drt_write_bmp(cfg.output_bmp, prm.width, prm.height, images[0]) != DRT_OK) return die_host("output bmp");
+        if(drt_write_bmp(cfg.average_bmp, prm.width, prm.height, images[1]) != DRT_OK) return die_host("average bmp");
+        if(drt_write_bmp(cfg.variance_bmp, prm.width, prm.height, images[2]) != DRT_OK) return die_host("variance bmp");
+    }
     printf("Converted.\n");
 
-    free(film.sum); free(film.mean); free(film.m2); free(film.filter);
+    for(int i = 0; i < 7; i += 1) { if(pinned) drt_cuda_host_free(blocks[i]); else free(blocks[i]); }
     for(int g = 0; g < gpus; g += 1) drt_cuda_destroy(ctxs[g]);
     return 0;
 }

@@ -111,6 +111,14 @@ int  drt_cuda_render_host(drt_cuda_context *ctx, const drt_render_params *params
  * stay idle.  count = 1 is render_host. */
 int  drt_cuda_render_host_multi(drt_cuda_context **contexts, int count, const drt_render_params *params, const drt_film *film_host);
 
+/* The same, plus the three 8-bit images of win32_main.c:150-152 (sum / filter, mean, M2 / per-pixel max; packed BGRA as drt_write_bmp
+ * takes them) converted ON THE DEVICES from the merged film -- fused into the merge kernel when several devices take part -- and copied
+ * to the three host buffers of width * height words: the Linux main writes the .bmp files from these instead of re-reading the .spd
+ * files it just wrote (9.4 GB each at 4096 x 4096) and converting on the CPU.  f32 arithmetic: bytes may differ by 1 from the f64
+ * conversion of drt_spd_to_rgb. */
+int  drt_cuda_render_host_multi_images(drt_cuda_context **contexts, int count, const drt_render_params *params, const drt_film *film_host,
+                                       uint32_t *bgra_sum_host, uint32_t *bgra_mean_host, uint32_t *bgra_var_host);
+
 /* Which render kernel the uploaded scene and the geometry precision select, for logs and benchmark lines:
  * name = "drt::render_kernel<float,5,true,true>" style string (geometry type, wavelength slots per half-warp lane, all-plastic
  * specialisation, one-pixel-per-task shape), warps_per_cta and ctas_per_sm as launched for a film render with `params`. */
@@ -184,15 +192,25 @@ int  drt_cuda_film_merge_slices(drt_cuda_context *ctx, const drt_film *dst_devic
 
 /* The merge half of the scattered exchange with a SHARDED result: like drt_cuda_film_merge_slices, but the merged planes of
  * [pixel_begin, pixel_end) stay on this device in the caller's slice film (indexed from pixel_begin; a drt_cuda_film_alloc of
- * ceil(slice_pixels / width) rows), and nothing but the three images (if given; usually the root's memory) leaves the device. */
+ * ceil(slice_pixels / width) rows), and nothing but the three images (if given; usually the root's memory) leaves the device.
+ * [pixel_begin, pixel_end) may also be a part (a band) of the slice: staging and slice film stay indexed from the slice's first pixel. */
 int  drt_cuda_film_merge_slices_local(drt_cuda_context *ctx, const drt_film *slice_device, const drt_film *staging_device, int count, uint64_t slice_pixels,
                                       uint32_t width, uint32_t height, uint64_t pixel_begin, uint64_t pixel_end,
                                       uint32_t *bgra_sum, uint32_t *bgra_mean, uint32_t *bgra_var, void *stream);
 
-/* Four stream-ordered device -> host copies of a merged slice into a WHOLE host film (pinned for the copies to overlap) at the
- * slice's global pixel positions: every rank reads its own slice back over its own PCIe link. */
-int  drt_cuda_film_read_slice(drt_cuda_context *ctx, const drt_film *slice_device, uint64_t pixel_begin, uint64_t pixel_end,
+/* Four stream-ordered device -> host copies of (a part of) a merged slice into a WHOLE host film (pinned for the copies to overlap) at
+ * the pixels' global positions: every rank reads its own slice back over its own PCIe link.  slice_device is indexed from pixel
+ * slice_begin (the first pixel of the owner's slice); [pixel_begin, pixel_end) is the part to copy. */
+int  drt_cuda_film_read_slice(drt_cuda_context *ctx, const drt_film *slice_device, uint64_t slice_begin, uint64_t pixel_begin, uint64_t pixel_end,
                               const drt_film *film_host, void *stream);
+
+/* A BAND of drt_cuda_render_device_scatter: the same part [band_begin, band_end) (pixel offsets inside a slice) of EVERY owner's slice,
+ * i.e. pixels o * slice_pixels + band_begin ... for o = 0 .. count - 1.  Rendering a frame band by band lets every owner merge
+ * (drt_cuda_film_merge_slices_local on the band's part of its slice) and read back band b on a second stream while band b + 1
+ * renders: the PCIe read-back hides under the render.  Needs >= 32 samples per pixel.  keep_stats != 0 adds this launch's work
+ * counters to the previous launch's (one drt_cuda_get_stats for all bands of a frame). */
+int  drt_cuda_render_device_scatter_band(drt_cuda_context *ctx, const drt_render_params *params, const drt_film *staging_device, int count, int rank,
+                                         uint64_t slice_pixels, uint64_t band_begin, uint64_t band_end, int keep_stats, void *stream);
 
 /* Device-side arrival flags, the exchange's only synchronisation (no host barrier between the render and the merge):
  * _signal: one tiny kernel on `stream` that, after everything enqueued before it on the stream has completed, fences system-wide and

@@ -246,7 +246,7 @@ def test_sharded_exchange_with_device_flags(ctx, ranks, w, h):
             ctx.flags_wait(flags[r] + 4 * 16 * par, ranks, epoch, stream=sp)
             ctx.film_merge_slices_local(slices[r], staging[par][r], ranks, slice_px, w, h, p0, p1, bgra=[t.data_ptr() for t in imgs], stream=sp)
             if epoch == 2:
-                ctx.film_read_slice(slices[r], p0, p1, host_film, stream=sp)
+                ctx.film_read_slice(slices[r], p0, p0, p1, host_film, stream=sp)
     torch.cuda.synchronize()
     assert ctx.flags_timeouts() == 0
     whole = film_mod.FilmPlanes(w, h, n, dev)
@@ -261,6 +261,62 @@ def test_sharded_exchange_with_device_flags(ctx, ranks, w, h):
     a, b = imgs[1].cpu().numpy().view(np.uint32), ref_img.cpu().numpy().view(np.uint32)
     assert max(np.abs(((a >> s) & 255).astype(int) - ((b >> s) & 255).astype(int)).max() for s in (0, 8, 16)) <= 1
     for f in staging[0] + staging[1] + slices:
+        ctx.film_free(f)
+    for b_ in flags:
+        ctx.buffer_free(b_)
+
+
+@pytest.mark.parametrize("ranks,w,h", [(2, 40, 24), (3, 37, 23)])
+def test_banded_scatter_merge_and_read_back(ctx, ranks, w, h):
+    """The end-to-end pipeline of the sharded exchange, emulated on one device: the frame is rendered in BANDS (the same part of every
+    owner's slice per band, drt_cuda_render_device_scatter_band) on a render stream per "rank"; on a copy stream per rank the band's part
+    of the own slice is merged and read back while the next band renders.  The host film equals the single render of all samples, and
+    the work counters of the bands add up."""
+    import torch
+    depth, per = 4, 32
+    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, per * ranks, depth)
+    ctx.upload_scene(scene, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    n = scene.num_wavelengths
+    npix = w * h
+    slice_px, parts = film_mod.slice_partition(npix, ranks)
+    rows = -(-slice_px * ranks // w)
+    staging = [ctx.film_alloc(w, rows) for _ in range(ranks)]
+    slices = [ctx.film_alloc(w, max(1, -(-slice_px // w))) for _ in range(ranks)]
+    flags = [ctx.buffer_alloc(64 * 4) for _ in range(ranks)]
+    host = {k: np.zeros((npix, n) if k != "filter" else npix, np.float32) for k in ("sum", "filter", "mean", "m2")}
+    host_film = cuda.Film(host["sum"].ctypes.data, host["filter"].ctypes.data, host["mean"].ctypes.data, host["m2"].ctypes.data)
+    render = [torch.cuda.Stream() for _ in range(ranks)]
+    copy = [torch.cuda.Stream() for _ in range(ranks)]
+    cuts = film_mod.ShardedFilmGroup.BAND_CUTS
+    paths = 0
+    for b in range(len(cuts) - 1):
+        b0, b1 = slice_px * cuts[b] // 16, slice_px * cuts[b + 1] // 16
+        if b1 <= b0:
+            continue
+        for r in range(ranks):
+            prm = oracledriver.params(w, h, r * per, (r + 1) * per, depth, cfg.pixel_scheme, 21)
+            ctx.render_device_scatter_band(prm, staging, r, slice_px, b0, b1, keep_stats=False, stream=render[r].cuda_stream)
+            ctx.flags_signal([f + 4 * r for f in flags], b + 1, stream=render[r].cuda_stream)
+            torch.cuda.synchronize()            # one context serves all emulated ranks: read each launch's counters before the next
+            paths += ctx.stats().paths
+        for r in range(ranks):
+            p0, p1 = parts[r]
+            q0, q1 = min(p1, p0 + b0), min(p1, p0 + b1)
+            ctx.flags_wait(flags[r], ranks, b + 1, stream=copy[r].cuda_stream)
+            if q1 > q0:
+                ctx.film_merge_slices_local(slices[r], staging[r], ranks, slice_px, w, h, q0, q1, stream=copy[r].cuda_stream)
+                ctx.film_read_slice(slices[r], p0, q0, q1, host_film, stream=copy[r].cuda_stream)
+    torch.cuda.synchronize()
+    assert ctx.flags_timeouts() == 0
+    assert paths == npix * per * ranks
+    whole = film_mod.FilmPlanes(w, h, n, torch.device("cuda", 0))
+    ctx.render_device(oracledriver.params(w, h, 0, per * ranks, depth, cfg.pixel_scheme, 21), whole.as_drt_film())
+    torch.cuda.synchronize()
+    assert np.array_equal(host["filter"], whole.filter.cpu().numpy())
+    for name in ("sum", "mean", "m2"):
+        assert _rel(host[name], getattr(whole, name).cpu().numpy()).max() < 2e-4, name
+    for f in staging + slices:
         ctx.film_free(f)
     for b_ in flags:
         ctx.buffer_free(b_)
