@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = --spp samples per pixel IN TOTAL, spp/N per GPU (the north-star workload, default); "
                          "weak = --spp samples per pixel PER GPU (an N*spp image).  The other mode is reported as an extra key.")
+    ap.add_argument("--spp-sweep", default="", help="comma-separated samples-per-pixel values measured after the main workload "
+                                                    "(BASELINE configs[2]: 1,4,16,64,256,1024), reported under spp_sweep")
     ap.add_argument("--no-other-scaling", action="store_true", help="skip the extra measurement in the other scaling mode")
     ap.add_argument("--merge", default="sharded", choices=["sharded", "nccl"],
                     help="multi-GPU film combination: sharded = render kernel scatters finished pixels to their owner over NVLink, "
@@ -496,6 +498,21 @@ def run_b200_arm(a):
             other = {"scaling": "weak" if a.scaling == "strong" else "strong", "samples_per_pixel_total": per * world,
                      "value": npix * per * world / (ms2 * 1e-3), "unit": "paths/s", "ms_per_step": ms2}
 
+    # ---- sample-count sweep (BASELINE configs[2]): for every value the frame with that many samples per pixel IN TOTAL, split over
+    # the GPUs when it divides (strong), and with that many PER GPU (weak); same timing rules, fewer steps for the long ones
+    sweep = []
+    for v in [int(x) for x in a.spp_sweep.split(",") if x.strip()]:
+        entry = {"spp": v}
+        for mode, per in (("strong", v // world if v % world == 0 else 0), ("weak", v)):
+            if per < 1 or (mode == "weak" and world == 1):
+                continue
+            pv = params_for(per)
+            for _ in range(3):
+                step(pv)
+            ms_v, _, _ = timed(pv, max(2, min(a.steps, 5)))
+            entry[mode] = {"samples_per_pixel_total": per * world, "ms_per_step": ms_v, "value": npix * per * world / (ms_v * 1e-3)}
+        sweep.append(entry)
+
     # ---- end to end through host buffers, every step: scene upload (H2D) + render + exchange + film read-back (D2H).
     # N = 1: the C-ABI host-buffer call drt_cuda_render_host.  N > 1 (sharded): every rank reads ITS merged slice back into one
     # shared page-locked host film over its own PCIe link (drt_cuda_film_read_slice); nccl: rank 0 reads the whole film back.
@@ -630,6 +647,9 @@ def run_b200_arm(a):
         }
         if other is not None:
             line[other["scaling"]] = other
+        if sweep:
+            line["spp_sweep"] = {"unit": "paths/s", "note": "whole frames at other sample counts, same scene and image size; strong = that many samples "
+                                 "per pixel in total split over the GPUs (where it divides), weak = that many per GPU", "points": sweep}
         if not a.no_cpu_baseline:
             try:
                 arm = CpuArm(a)

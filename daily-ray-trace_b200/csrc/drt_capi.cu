@@ -66,7 +66,7 @@ extern "C" void drt_cuda_destroy(drt_cuda_context *ctx)
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_geom32); cudaFree(ctx->d_geom64); cudaFree(ctx->d_index); cudaFree(ctx->d_pool);
-    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats_ring); cudaFree(ctx->d_counter_ring); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice);
+    cudaFree(ctx->d_rgb_tables); cudaFree(ctx->d_stats_ring); cudaFree(ctx->d_counter_ring); cudaFree(ctx->d_film); cudaFree(ctx->d_dump); cudaFree(ctx->d_slice); cudaFree(ctx->d_deep);
     drt_exchange_release(ctx);
     if(ctx->band_render) cudaStreamDestroy(ctx->band_render);
     if(ctx->band_copy) cudaStreamDestroy(ctx->band_copy);
@@ -630,30 +630,48 @@ extern "C" int drt_cuda_film_sizes(const drt_cuda_context *ctx, uint32_t width, 
 static int kernel_mode(const drt_cuda_context *ctx) { return ctx->f64_geometry ? 0 : ctx->all_fast ? 1 : ctx->classed ? 2 : 0; }
 
 /* record layout of a render with `max_depth` bounces (RenderLaunch in drt_device.cuh) */
-static void record_layout(const drt_cuda_context *ctx, uint32_t max_depth, RenderLaunch &L)
+static void record_layout(const drt_cuda_context *ctx, uint32_t max_depth, uint32_t smem_depth, RenderLaunch &L)
 {
     L.eval_words = (uint32_t)ctx->eval_words;
     const bool compact = kernel_mode(ctx) != 0;   /* the plastic-only and the classed kernel and their compact records */
     L.bounce_words = (2 + (uint32_t)ctx->nlights * (L.eval_words + 1) + L.eval_words + 3u) & ~3u;
     if(L.bounce_words < 8) L.bounce_words = 8;
     L.head_words = 4;
-    if(compact) { L.bounce_words = 4; L.head_words = (2 + (max_depth + 1) / 2 + 3u) & ~3u; }
-    L.path_words = L.head_words + max_depth * L.bounce_words;
+    if(smem_depth > max_depth) smem_depth = max_depth;
+    if(compact) { L.bounce_words = 4; L.head_words = (2 + (smem_depth + 1) / 2 + 3u) & ~3u; }
+    L.smem_depth = smem_depth;
+    L.path_words = L.head_words + smem_depth * L.bounce_words;      /* the shared-memory part of a record */
     L.path_stride = ((L.path_words / 4) & 1u) ? L.path_words : L.path_words + 4;
+    /* bounces past smem_depth: the slot's overflow row in global memory (RenderLaunch::deep) */
+    const uint32_t over = max_depth - smem_depth;
+    L.deep_hdr_off = over * L.bounce_words;
+    L.deep_stride = over ? ((L.deep_hdr_off + (compact ? (over + 1) / 2 : 0u) + 4u + 3u) & ~3u) : 0u;
 }
 
-/* path records live in shared memory: use as many warps per CTA (the kernel's full count, then halves) as the record size
- * allows, and as many CTAs per SM as shared memory and the register budget of the kernel's __launch_bounds__ allow */
-static bool launch_shape(const drt_cuda_context *ctx, const RenderLaunch &L, int *warps_out, int *ctas_out, size_t *smem_out)
+/* Path records live in shared memory.  A record holds as many bounces as fit with the kernel's full number of warps and CTAs per SM
+ * (smem_depth); deeper bounces overflow to global memory, so neither max_cast_depth nor the number of lights limits a render
+ * (cast_ray loops `depth < max_depth` without a bound, daily_ray_trace.c:446).  whole = true (record dumps): the whole record must
+ * sit in shared memory, with fewer warps per CTA if need be. */
+static bool launch_shape(const drt_cuda_context *ctx, uint32_t max_depth, bool whole, RenderLaunch &L, int *warps_out, int *ctas_out, size_t *smem_out)
 {
-    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, kernel_mode(ctx));
+    const int mode = kernel_mode(ctx);
+    const int full_warps = drt_render_cta_warps(ctx->f64_geometry, mode), want_ctas = drt_render_min_ctas(ctx->f64_geometry, mode);
+    auto bytes = [&](uint32_t depth, int warps) { record_layout(ctx, max_depth, depth, L); return drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); };
     int warps = full_warps;
-    size_t smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots);
-    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = drt_render_smem_bytes(L, ctx->f64_geometry, warps, ctx->nslots); }
+    uint32_t depth = max_depth;
+    const size_t per_cta = (size_t)(227 * 1024) / (size_t)want_ctas - 1024;
+    if(!whole && max_depth > 1 && bytes(max_depth, warps) > per_cta)
+    {
+        uint32_t lo = 1, hi = max_depth;          /* largest depth whose records fit with full occupancy (bytes() grows with depth) */
+        while(lo < hi) { uint32_t mid = (lo + hi + 1) / 2; if(bytes(mid, warps) <= per_cta) lo = mid; else hi = mid - 1; }
+        depth = lo;
+    }
+    size_t smem = bytes(depth, warps);
+    while(smem > ctx->smem_optin && warps > 1) { warps /= 2; smem = bytes(depth, warps); }
     *warps_out = warps; *smem_out = smem;
     if(smem > ctx->smem_optin) return false;
     int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    int by_threads = (drt_render_min_ctas(ctx->f64_geometry, kernel_mode(ctx)) * full_warps) / warps;
+    int by_threads = (want_ctas * full_warps) / warps;
     if(ctas_per_sm > by_threads) ctas_per_sm = by_threads;
     if(ctas_per_sm < 1) ctas_per_sm = 1;
     *ctas_out = ctas_per_sm;
@@ -668,13 +686,12 @@ extern "C" int drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_rend
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.pool_words = ctx->pool_words;
-    record_layout(ctx, max_depth, L);
     int warps = 0, ctas = 0;
     size_t smem = 0;
-    if(!launch_shape(ctx, L, &warps, &ctas, &smem)) return fail(DRT_CUDA_E_UNSUPPORTED, "records of max_cast_depth %u do not fit in shared memory", max_depth);
+    if(!launch_shape(ctx, max_depth, false, L, &warps, &ctas, &smem)) return fail(DRT_CUDA_E_UNSUPPORTED, "one bounce record of this scene does not fit in shared memory");
     if(name && name_len)
-        snprintf(name, name_len, "drt::render_kernel<%s,%d,%d,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
-                 kernel_mode(ctx), (params->sample_end - params->sample_begin >= 32) ? "true" : "false");
+        snprintf(name, name_len, "drt::render_kernel<%s,%d,%d,%s,%s>", ctx->f64_geometry ? "double" : "float", ctx->nslots,
+                 kernel_mode(ctx), (params->sample_end - params->sample_begin >= 32) ? "true" : "false", L.deep_stride ? "true" : "false");
     if(warps_per_cta) *warps_per_cta = warps;
     if(ctas_per_sm) *ctas_per_sm = ctas;
     return DRT_CUDA_OK;
@@ -725,13 +742,14 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     /* max_cast_depth 0 casts no ray at all (cast_ray's loop, daily_ray_trace.c:446): nothing to cull, and the culled pixels' "one closest-hit ray" must not be counted */
     hit_rect(ctx->hit_bound && p->max_depth > 0, ctx->hit_u0, ctx->hit_u1, ctx->hit_v0, ctx->hit_v1, p->width, p->height, rect);
     L.hit_x0 = rect[0]; L.hit_y0 = rect[1]; L.hit_x1 = rect[2]; L.hit_y1 = rect[3];
-    record_layout(ctx, p->max_depth, L);
-    if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
+    /* record dumps (diagnostics) want the whole record in shared memory; renders keep full occupancy and let deep bounces overflow */
+    const bool whole = record_dump != nullptr || (path_words_out != nullptr && !dump && !film.sum);
     int warps, ctas_per_sm;
     size_t smem;
-    if(!launch_shape(ctx, L, &warps, &ctas_per_sm, &smem))
-        return fail(DRT_CUDA_E_UNSUPPORTED, "max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
-                    p->max_depth, ctx->nlights, smem, ctx->smem_optin);
+    if(!launch_shape(ctx, p->max_depth, whole, L, &warps, &ctas_per_sm, &smem))
+        return fail(DRT_CUDA_E_UNSUPPORTED, "%s: max_cast_depth %u with %d lights needs %zu bytes of shared memory per warp (limit %zu)",
+                    whole ? "record dump" : "render", p->max_depth, ctx->nlights, smem, ctx->smem_optin);
+    if(path_words_out) { *path_words_out = L.path_words; if(!record_dump && !dump && !film.sum) return DRT_CUDA_OK; }
     uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
     const bool band = band_end > band_begin;
     if(band)
@@ -747,6 +765,15 @@ static int launch(drt_cuda_context *ctx, const drt_render_params *p, uint32_t x0
     uint64_t grid = (uint64_t)ctx->num_sms * ctas_per_sm;
     uint64_t need = (ntasks + warps - 1) / warps;
     if(grid > need) grid = need;
+    if(L.deep_stride)
+    {
+        /* overflow rows of every resident warp; the buffer only grows.  (Renders of one context that are in flight on different
+         * streams would share it: deep renders are one at a time per context.) */
+        const size_t need_bytes = (size_t)grid * (size_t)warps * DRT_WARP * L.deep_stride * 4;
+        int rc = drt_ensure_buffer(&ctx->d_deep, &ctx->deep_bytes, need_bytes);
+        if(rc != DRT_CUDA_OK) return rc;
+        L.deep = ctx->d_deep;
+    }
     if(!keep_stats)
     {
         ctx->d_stats = ctx->d_stats_ring + (ctx->stats_calls++ % DRT_RING);

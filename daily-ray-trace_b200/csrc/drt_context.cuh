@@ -60,6 +60,7 @@ struct drt_cuda_context
     /* library-owned film + dump buffers for the host-buffer entry points */
     float *d_film = nullptr; size_t film_bytes = 0;
     float *d_dump = nullptr; size_t dump_bytes = 0;
+    float *d_deep = nullptr; size_t deep_bytes = 0;     /* overflow rows of deep renders (RenderLaunch::deep) */
     float *d_slice = nullptr; size_t slice_bytes = 0;   /* merged planes of this rank's slice before they are copied to the root */
     uint64_t launches = 0;
     size_t upload_bytes = 0;

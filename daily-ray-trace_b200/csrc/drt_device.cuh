@@ -195,6 +195,13 @@ struct RenderLaunch
     uint32_t path_words;           /* head_words + max_depth*bounce_words */
     uint32_t path_stride;          /* words between the records of consecutive slots: >= path_words, 4 * odd */
     uint32_t geom_bytes, pool_words;
+    /* Deep renders: only the first smem_depth bounces of a path live in its shared-memory record (as many as fit with the kernel's
+     * full number of warps); bounces from smem_depth on go to the slot's OVERFLOW ROW in global memory: row (warp * 32 + slot) of
+     * `deep`, deep_stride words each -- (max_depth - smem_depth) bounces of bounce_words words, and for compact records their 16-bit
+     * headers from word deep_hdr_off.  The rows are written and read once per path by the warp that owns them, so they stay in L2.
+     * smem_depth = max_depth (and deep = NULL) for renders whose records fit, i.e. every shipped configuration. */
+    uint32_t smem_depth, deep_stride, deep_hdr_off;
+    float   *deep;
     /* scattered film store (multi-GPU, drt_cuda_render_device_scatter): pixel p belongs to rank p / scatter_slice, and this
      * rank's partial film of it is written -- over NVLink when the owner is a peer -- into the owner's staging film at pixel
      * scatter_rank * scatter_slice + p % scatter_slice, so every owner ends up with all ranks' partial films of its slice in

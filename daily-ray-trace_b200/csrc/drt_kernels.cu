@@ -5,19 +5,21 @@
 #include <cuda_runtime.h>
 #include "drt_device.cuh"
 
-cudaError_t drt_launch_render_f32_fast(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-cudaError_t drt_launch_render_f32_classed(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-cudaError_t drt_launch_render_f32_general(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
-cudaError_t drt_launch_render_f64(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream);
+#define DRT_DECLARE(NAME) cudaError_t NAME(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
+DRT_DECLARE(drt_launch_render_f32_fast);    DRT_DECLARE(drt_launch_render_f32_fast_deep);
+DRT_DECLARE(drt_launch_render_f32_classed); DRT_DECLARE(drt_launch_render_f32_classed_deep);
+DRT_DECLARE(drt_launch_render_f32_general); DRT_DECLARE(drt_launch_render_f32_general_deep);
+DRT_DECLARE(drt_launch_render_f64);         DRT_DECLARE(drt_launch_render_f64_deep);
 
-/* f64 geometry is the branch-flip diagnostic: it always runs the general kernel */
+/* f64 geometry is the branch-flip diagnostic: it always runs the general kernel.  A launch whose records overflow to global memory
+ * (L.deep_stride != 0) takes the deep instantiation of its mode. */
 cudaError_t drt_launch_render(const RenderLaunch &L, bool f64_geometry, int mode, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
-    const bool paired = L.pixels_per_task == 1;
-    if(f64_geometry) return drt_launch_render_f64(L, paired, nslots, grid, warps, smem, stream);
-    return mode == 1 ? drt_launch_render_f32_fast(L, paired, nslots, grid, warps, smem, stream)
-         : mode == 2 ? drt_launch_render_f32_classed(L, paired, nslots, grid, warps, smem, stream)
-                     : drt_launch_render_f32_general(L, paired, nslots, grid, warps, smem, stream);
+    const bool paired = L.pixels_per_task == 1, deep = L.deep_stride != 0;
+    if(f64_geometry) return deep ? drt_launch_render_f64_deep(L, paired, nslots, grid, warps, smem, stream) : drt_launch_render_f64(L, paired, nslots, grid, warps, smem, stream);
+    if(mode == 1) return deep ? drt_launch_render_f32_fast_deep(L, paired, nslots, grid, warps, smem, stream) : drt_launch_render_f32_fast(L, paired, nslots, grid, warps, smem, stream);
+    if(mode == 2) return deep ? drt_launch_render_f32_classed_deep(L, paired, nslots, grid, warps, smem, stream) : drt_launch_render_f32_classed(L, paired, nslots, grid, warps, smem, stream);
+    return deep ? drt_launch_render_f32_general_deep(L, paired, nslots, grid, warps, smem, stream) : drt_launch_render_f32_general(L, paired, nslots, grid, warps, smem, stream);
 }
 
 int drt_render_cta_warps(bool f64_geometry, int mode)

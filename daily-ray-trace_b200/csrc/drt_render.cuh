@@ -639,8 +639,8 @@ __device__ __forceinline__ void sample_direction(const GeomT<R> &g, const Hit<R>
 /* ------------------------------------------------------------------ phase 1: trace one path, emit its record
  * `rec` points at this lane's record (16-byte aligned).  Returns the termination-histogram bin and a class bit. */
 
-template <typename R, int MODE>
-__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec,
+template <typename R, int MODE, bool DEEP>
+__device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex &ix, const RenderLaunch &L, float *rec, float *deep,
                                                uint32_t x, uint32_t y, uint32_t sample, uint32_t (&tally)[4])
 {
     constexpr bool ALLFAST = MODE != 0;    /* compact records: the plastic-only kernel (1) and the classed kernel (2) */
@@ -688,13 +688,16 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         bool found = closest_hit<R>(g, o, d, skip, h);
         int m = found ? h.surf_mat : g.escape_mat;
         int flags = g.mflags[m];
-        uint32_t base = REC_HEAD + nb * bw;
+        /* this bounce's words: in the slot's shared-memory record, or (DEEP instantiations: renders whose records do not fit) -- past
+         * the L.smem_depth bounces that fit there -- in the slot's global overflow row `deep` (RenderLaunch::deep) */
+        const bool in_smem = !DEEP || nb < L.smem_depth;
+        float *rb = in_smem ? rec + REC_HEAD + nb * bw : deep + (nb - L.smem_depth) * bw;
         if(flags & 1)   /* black body: escape or emitter, cast_ray :451-457 */
         {
             if(flags & 2)
             {
                 if(ALLFAST) emitter = (uint32_t)(m + 1) << 16;   /* compact records: the closing emitter rides in word 0 */
-                else { rec[base] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3)); nb += 1; }   /* Q6 */
+                else { rb[0] = __uint_as_float(KIND_EMIT | ((uint32_t)m << 3)); nb += 1; }   /* Q6 */
             }
             end_depth = depth;
             break;
@@ -709,7 +712,7 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
         const bool plastic = ALLFAST ? (cls == DRT_CLASS_PLASTIC) : (g.bmask[sm] == BMASK_PLASTIC && g.nlobes[sm] == 2);
         const bool fast = ALLFAST || (plastic && ix.plastic[sm] != 0);
         const int nlights = ALLFAST ? 1 : g.nlights;
-        float *recw = rec + L.head_words + 4u * nb;   /* this bounce's four words in a compact record */
+        float *recw = in_smem ? rec + L.head_words + 4u * nb : deep + 4u * (nb - L.smem_depth);   /* this bounce's four words in a compact record */
         if(CLASSED && cls == DRT_CLASS_ROUGH) { recw[0] = 0.f; recw[1] = 1.f; }   /* the light may turn out hidden */
         /* K3: direct_light_contribution, :272-332 -- every emissive surface in index order; draws come before visibility */
         uint32_t vis_mask = 0;
@@ -747,11 +750,11 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
             V3<R> ldir;
             if(visible<R>(g, h.pos, lp, h.plane_slot, ldir))
             {
-                const uint32_t e = base + 2 + (ew + 1) * (uint32_t)j;
+                const uint32_t e = 2 + (ew + 1) * (uint32_t)j;
                 if(plastic)
                 {
                     plastic_weights<R>(g, sm, h.nrm, h.out, ldir, fast ? (float)k : 1.f, wd_n, wg_n);
-                    if(!fast) { rec[e] = wd_n; rec[e + 1] = wg_n; }
+                    if(!fast) { rb[e] = wd_n; rb[e + 1] = wg_n; }
                 }
                 else if(CLASSED)
                 {
@@ -763,18 +766,18 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                         recw[0] = wc.x * (float)k; recw[1] = wc.y;
                     }
                 }
-                else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, 1.f, rec, e);
-                if(!fast) rec[e + ew] = (float)k;
+                else eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, ldir, 0, 1.f, rb, e);
+                if(!fast) rb[e + ew] = (float)k;
                 vis_mask |= 1u << j;
             }
         }
         /* K4: sample the next direction and evaluate the BSDF for it, cast_ray :464-472 */
         V3<R> in; R inv_pdf; int match;
         sample_direction<R>(g, h, rng, in, inv_pdf, match);
-        const uint32_t es = base + 2 + (ew + 1) * (uint32_t)nlights;
+        const uint32_t es = 2 + (ew + 1) * (uint32_t)nlights;
         float wd_s = 0.f, wg_s = 0.f;
         if(plastic) plastic_weights<R>(g, sm, h.nrm, h.out, in, (float)inv_pdf, wd_s, wg_s);
-        else if(!CLASSED) eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rec, es);
+        else if(!CLASSED) eval_weights_general<R>(g, sm, h.nrm, h.out, h.on_dot, in, match, (float)inv_pdf, rb, es);
         if(ALLFAST)
         {
             uint32_t hdr16;
@@ -805,21 +808,22 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                     hdr16 = (uint32_t)DRT_CLASS_SPECULAR | (basis << 2) | (inside << 4) | ((uint32_t)sm << 5);
                 }
             }
-            reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)hdr16;
+            if(in_smem) reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)hdr16;
+            else reinterpret_cast<uint16_t *>(deep + L.deep_hdr_off)[nb - L.smem_depth] = (uint16_t)hdr16;
         }
         else if(fast)
         {
-            float4 *r4 = reinterpret_cast<float4 *>(rec + base);
+            float4 *r4 = reinterpret_cast<float4 *>(rb);
             r4[0] = make_float4(__uint_as_float(KIND_SHADE | HDR_FAST | ((uint32_t)ix.plastic[sm] << 2)), wd_n, wg_n, 0.f);
             r4[1] = make_float4(wd_s, wg_s, 0.f, 0.f);
         }
         else
         {
             general = 1;
-            if(plastic) { rec[es] = wd_s; rec[es + 1] = wg_s; }
+            if(plastic) { rb[es] = wd_s; rb[es + 1] = wg_s; }
             uint32_t swapped = (h.inc_mat != g.base_mat) ? 1u : 0u;
-            rec[base] = __uint_as_float(KIND_SHADE | ((uint32_t)sm << 3) | (swapped << 8) | (vis_mask << 16));
-            rec[base + 1] = (float)h.on_dot;
+            rb[0] = __uint_as_float(KIND_SHADE | ((uint32_t)sm << 3) | (swapped << 8) | (vis_mask << 16));
+            rb[1] = (float)h.on_dot;
         }
         nb += 1;
         d = in;
@@ -1055,8 +1059,8 @@ static __device__ __noinline__ Carry<NS> shade_special(uint32_t hdr, float4 w, c
  *     radiance   += throughput * (wd_n k * DE + wg_n k * GE)        (NEE: bdsf * emission * k, :322-327; weights are 0 when shadowed)
  *     throughput *= wd_s/pdf * D + wg_s/pdf * G                      (:467-469)
  * with D, G, DE = D*E, GE = G*E fetched from the material's interleaved plastic block by 16-byte loads. */
-template <int NS, int MODE, typename G>
-__device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool, const float *pool_lane,
+template <int NS, int MODE, bool DEEP, typename G>
+__device__ __forceinline__ void replay_path(const float *col, const float *deep, uint32_t nb, const G &g, const SpdIndex &ix, const float *pool, const float *pool_lane,
                                             uint32_t lane16, const RenderLaunch &L, float (&c)[NS])
 {
     constexpr bool ALLFAST = MODE != 0, CLASSED = MODE == 2;
@@ -1080,10 +1084,16 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
             for(int k = 0; k < NP; k += 1) thr2[k] = ep[k * DRT_HALF];
             if(NS & 1) thr1 = reinterpret_cast<const float *>(ep + NP * DRT_HALF)[0];
         }
+        /* The bounces come in at most two spans: the first L.smem_depth in the slot's shared-memory record, the rest (deep renders
+         * only) in the slot's global overflow row. */
+        uint32_t left = nshade, span = DEEP ? min(nshade, L.smem_depth) : nshade;
+#pragma unroll 1
+        for(;;)
+        {
         uint32_t hdr = hp[0];
         float4 w = wp[0];   /* wd_n k, wg_n k, wd_s / pdf, wg_s / pdf */
 #pragma unroll 1
-        for(uint32_t b = 0; b < nshade; b += 1)
+        for(uint32_t b = 0; b < span; b += 1)
         {
             if constexpr(CLASSED)
             {
@@ -1127,6 +1137,12 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
                 thr1 *= fmaf(w1w, q.y, w1z * q.x);
             }
         }
+        left -= span;
+        if(!DEEP || left == 0u) break;
+        hp = reinterpret_cast<const uint16_t *>(deep + L.deep_hdr_off);
+        wp = reinterpret_cast<const float4 *>(deep);
+        span = left;
+        }
         if(nb >> 16)   /* the path ran into the light, cast_ray :453-457: radiance += throughput * E = u */
         {
 #pragma unroll
@@ -1137,17 +1153,18 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
     else
     {
     const uint32_t bw = L.bounce_words, ew = L.eval_words;
-    const float *p = col + REC_HEAD;
-    uint32_t base = REC_HEAD;
+    const float *p = (!DEEP || L.smem_depth) ? col + REC_HEAD : deep;
     float4 a_next = *reinterpret_cast<const float4 *>(p);
-    for(uint32_t b = 0; b < nb; b += 1, p += bw, base += bw)
+    for(uint32_t b = 0; b < nb; b += 1)
     {
         const float4 a = a_next;
-        if(b + 1 < nb) a_next = *reinterpret_cast<const float4 *>(p + bw);   /* next header in flight while this bounce is shaded */
+        const float *pc = p;
+        p = (DEEP && b + 1 == L.smem_depth) ? deep : p + bw;   /* past the bounces that fit in shared memory: the slot's global overflow row */
+        if(b + 1 < nb) a_next = *reinterpret_cast<const float4 *>(p);   /* next header in flight while this bounce is shaded */
         const uint32_t hdr = __float_as_uint(a.x);
         if((hdr & HDR_FAST) != 0u)
         {
-            const float4 s4 = *reinterpret_cast<const float4 *>(p + 4);
+            const float4 s4 = *reinterpret_cast<const float4 *>(pc + 4);
             const float4 *blk = reinterpret_cast<const float4 *>(pool) + (hdr >> 4) + lane16;
             const unsigned long long wdn = pk2(a.y, a.y), wgn = pk2(a.z, a.z), wds = pk2(s4.x, s4.x), wgs = pk2(s4.y, s4.y);
 #pragma unroll
@@ -1181,7 +1198,7 @@ __device__ __forceinline__ void replay_path(const float *col, uint32_t nb, const
 #pragma unroll
             for(int k = 0; k < NP; k += 1) { upk2(thr2[k], st.thr.v[2 * k], st.thr.v[2 * k + 1]); upk2(dst2[k], st.dst.v[2 * k], st.dst.v[2 * k + 1]); }
             if(NS & 1) { st.thr.v[NS - 1] = thr1; st.dst.v[NS - 1] = dst1; }
-            st = shade_bounce_general<NS, G>(col, base, hdr, g, ix, pool_lane, ew, L.nlights, st);
+            st = shade_bounce_general<NS, G>(pc, 0u, hdr, g, ix, pool_lane, ew, L.nlights, st);
 #pragma unroll
             for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(st.thr.v[2 * k], st.thr.v[2 * k + 1]); dst2[k] = pk2(st.dst.v[2 * k], st.dst.v[2 * k + 1]); }
             if(NS & 1) { thr1 = st.thr.v[NS - 1]; dst1 = st.dst.v[NS - 1]; }
@@ -1334,7 +1351,7 @@ static __device__ __noinline__ void dump_path(float *record_dump, float *path_du
 #define DRT_PARK_GENERAL 0   /* park the film of the general kernel too (pays off only if that buys resident warps) */
 #endif
 /* PAIRED: one pixel per task with all its samples (spp >= 32) against 32/spp whole pixels per task; see the task loop. */
-template <typename R, int NS, int MODE, bool PAIRED>
+template <typename R, int NS, int MODE, bool PAIRED, bool DEEP>
 __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_CLASSED_WARPS : DRT_CTA_WARPS) * DRT_WARP,
                                    MODE == 1 ? DRT_MIN_CTAS : MODE == 2 ? DRT_CLASSED_CTAS : DRT_GENERAL_CTAS) render_kernel(const RenderLaunch L)
 {
@@ -1382,6 +1399,8 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
     float *rec = srec + (size_t)warp * L.path_stride * DRT_WARP;   /* word w of slot s at rec[s * path_stride + w] */
     const uint32_t stride = L.path_stride;
     float *park = spark + (size_t)warp * (3 * NS + 2) * DRT_WARP + lane;
+    /* this warp's 32 overflow rows in global memory (deep renders: bounces past L.smem_depth; RenderLaunch::deep) */
+    float *deep_w = DEEP ? L.deep + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * DRT_WARP * L.deep_stride : nullptr;
     const float *pool_lane = spool + lane16;
     const uint32_t rw = L.x1 - L.x0, npix = rw * (L.y1 - L.y0);
     const uint32_t spp = L.sample_end - L.sample_begin;
@@ -1488,7 +1507,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
                 }
                 else
                 {
-                    uint32_t r = trace_path<R, MODE>(g, ix, L, rec + lane * stride, x, y, L.sample_begin + my_s, tally);
+                    uint32_t r = trace_path<R, MODE, DEEP>(g, ix, L, rec + lane * stride, deep_w + (size_t)lane * L.deep_stride, x, y, L.sample_begin + my_s, tally);
                     bin = r & 255u; general = r >> 8;
                 }
             }
@@ -1556,7 +1575,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
                     if(pos < lo + per_px)
                     {
                         float c[NS];
-                        replay_path<NS, MODE>(rec + slot * stride, nb, g, ix, spool, pool_lane, lane16, L, c);
+                        replay_path<NS, MODE, DEEP>(rec + slot * stride, deep_w + (size_t)slot * L.deep_stride, nb, g, ix, spool, pool_lane, lane16, L, c);
                         film.add(c);
                         if(dumping)
                         {
@@ -1601,15 +1620,17 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
 
 /* ------------------------------------------------------------------ launch helper of the instantiating translation units */
 
-template <typename R, int MODE, bool PAIRED>
+/* DEEP = the instantiation whose records overflow to global memory (RenderLaunch::deep); the instantiating translation units
+ * (drt_kernels_*.cu) build the shallow and the deep kernels of a mode separately so that the hot ones keep their register budget. */
+template <typename R, int MODE, bool PAIRED, bool DEEP>
 static cudaError_t drt_launch_render_ns(const RenderLaunch &L, int nslots, int grid, int warps, size_t smem, cudaStream_t stream)
 {
 #define DRT_LAUNCH(NS) do { \
-        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if(e != cudaSuccess) return e; \
-        e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        e = cudaFuncSetAttribute(drt::render_kernel<R, NS, MODE, PAIRED, DEEP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
         if(e != cudaSuccess) return e; \
-        drt::render_kernel<R, NS, MODE, PAIRED><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
+        drt::render_kernel<R, NS, MODE, PAIRED, DEEP><<<grid, warps * DRT_WARP, smem, stream>>>(L); } while(0)
     switch(nslots)   /* wavelength slots per lane of a half warp: N <= 32, 48, 80, 128 */
     {
         case 2: DRT_LAUNCH(2); break;
@@ -1620,3 +1641,11 @@ static cudaError_t drt_launch_render_ns(const RenderLaunch &L, int nslots, int g
 #undef DRT_LAUNCH
     return cudaGetLastError();
 }
+
+/* one translation unit = one (arithmetic type, mode, deep) combination, both task shapes */
+#define DRT_DEFINE_LAUNCHER(NAME, R, MODE, DEEP) \
+    cudaError_t NAME(const RenderLaunch &L, bool paired, int nslots, int grid, int warps, size_t smem, cudaStream_t stream) \
+    { \
+        return paired ? drt_launch_render_ns<R, MODE, true, DEEP>(L, nslots, grid, warps, smem, stream) \
+                      : drt_launch_render_ns<R, MODE, false, DEEP>(L, nslots, grid, warps, smem, stream); \
+    }

@@ -73,17 +73,33 @@ def test_sixteen_surfaces_many_lights(ctx, host, n_lights, depth):
     assert (common.path_errors(gpu, o_paths) <= 2e-4).mean() >= 0.99
 
 
-def test_deep_paths(ctx):
-    """max_cast_depth 12: records of 8 warps no longer fit in shared memory, the launcher drops to fewer warps per CTA."""
-    w, h, spp, depth = 24, 16, 3, 12
-    cfg, tables, scene, camera = common.load("cornell_plane_light", w, h, spp, depth)
-    ctx.upload_scene(scene, camera, tables)
-    ctx.set_geometry_precision(cuda.GEOMETRY_F64)
+@pytest.mark.parametrize("scene,depth,geometry", [("cornell_plane_light", 12, "f64"), ("init_cornell", 40, "f32"), ("classed_all", 24, "f32"),
+                                                  ("stress_all", 20, "f32"), ("cornell_large_box", 100, "f32")])
+def test_deep_paths(ctx, scene, depth, geometry):
+    """cast_ray loops `depth < max_depth` with no bound (daily_ray_trace.c:446).  A path record keeps as many bounces in shared memory as
+    fit at the kernel's full occupancy; deeper bounces overflow to the slot's row in global memory (RenderLaunch::deep), in all three
+    kernel modes (plastic-only, classed, general; f64 geometry = general).  Per-path radiance and the work counters against the oracle."""
+    w, h, spp = 24, 16, 3
+    cfg, tables, sc, camera = common.load(scene, w, h, spp, depth)
+    ctx.upload_scene(sc, camera, tables)
+    ctx.set_geometry_precision(cuda.GEOMETRY_F64 if geometry == "f64" else cuda.GEOMETRY_F32)
     prm = oracledriver.params(w, h, 0, spp, depth, cfg.pixel_scheme, 4)
     gpu = ctx.sample_paths(prm, 0, 0, w, h)
-    _, _, _, o_paths, cnt = oracledriver.render_tile(scene, camera, prm, 0, 0, w, h, want_paths=True)
-    assert ctx.stats().reached_depth_cap == cnt.reached_depth_cap
-    assert (common.path_errors(gpu, o_paths) <= 1e-3).mean() >= 0.99
+    st = ctx.stats()
+    _, _, _, o_paths, cnt = oracledriver.render_tile(sc, camera, prm, 0, 0, w, h, want_paths=True)
+    ok = (common.path_errors(gpu, o_paths) <= 1e-3).mean()
+    print(f"\n{scene} depth {depth}: {100 * ok:.2f} % of paths within 1e-3, {cnt.shaded_bounces / cnt.paths:.1f} bounces per path")
+    assert ok >= (0.99 if depth <= 24 else 0.97)       # a branch flip early in a 100-bounce path changes everything after it
+    if geometry == "f64":
+        assert st.reached_depth_cap == cnt.reached_depth_cap
+    assert abs(int(st.shaded_bounces) - int(cnt.shaded_bounces)) <= 0.02 * cnt.shaded_bounces + 8
+    # the same render as a film (the render kernel proper, several warps with overflow rows)
+    film = ctx.render_host(prm)
+    o_sum = oracledriver.render_tile(sc, camera, prm, 0, 0, w, h)[0]
+    n = sc.num_wavelengths
+    rel = np.abs(film["sum"] - o_sum[:, :n]) / np.maximum(np.abs(o_sum[:, :n]), 1e-4 * np.abs(o_sum[:, :n]).max())
+    assert (rel.max(axis=1) <= 5e-3).mean() >= 0.9
+    ctx.set_geometry_precision(cuda.GEOMETRY_F32)
 
 
 def test_error_codes(ctx):
@@ -100,8 +116,11 @@ def test_error_codes(ctx):
         with pytest.raises(cuda.CudaError) as e:
             ctx.render_host(bad)
         assert e.value.code == -103
-    with pytest.raises(cuda.CudaError) as e:          # depth x lights beyond what shared memory can hold: loud, not silent
-        ctx.sample_paths(oracledriver.params(w, h, 0, 1, 4000), 0, 0, 1, 1)
+    # depth x lights no longer limits a render (deep bounces overflow to global memory); only the record DUMP, a diagnostic that
+    # wants a whole record in shared memory, still says so loudly
+    assert ctx.sample_paths(oracledriver.params(w, h, 0, 1, 4000), 0, 0, 1, 1).shape == (1, 1, 69)
+    with pytest.raises(cuda.CudaError) as e:
+        ctx.debug_records(oracledriver.params(w, h, 0, 1, 4000), 0, 0, 1, 1)
     assert e.value.code == -104 and b"shared memory" in L.drt_cuda_last_error()
     with pytest.raises(cuda.CudaError):
         cuda.Context(99)
@@ -144,7 +163,10 @@ def test_kernel_selection(ctx, scene, mode):
     ctx.set_geometry_precision(cuda.GEOMETRY_F32)
     prm = oracledriver.params(32, 32, 0, 32, 4, cfg.pixel_scheme, 1)
     name, warps, ctas = ctx.render_kernel_info(prm)
-    assert name == f"drt::render_kernel<float,5,{mode},true>", name
+    assert name == f"drt::render_kernel<float,5,{mode},true,false>", name
     ctx.set_geometry_precision(cuda.GEOMETRY_F64)
-    assert ctx.render_kernel_info(prm)[0] == "drt::render_kernel<double,5,0,true>"
+    assert ctx.render_kernel_info(prm)[0] == "drt::render_kernel<double,5,0,true,false>"
     ctx.set_geometry_precision(cuda.GEOMETRY_F32)
+    # a render whose records do not fit in shared memory at full occupancy takes the mode's deep instantiation (same warps per CTA)
+    deep = ctx.render_kernel_info(oracledriver.params(32, 32, 0, 32, 64, cfg.pixel_scheme, 1))
+    assert deep[0] == f"drt::render_kernel<float,5,{mode},true,true>" and deep[1:] == (warps, ctas), deep
