@@ -35,7 +35,7 @@
 #ifndef DRT_LOCKSTEP
 #define DRT_LOCKSTEP 2         /* bit mask of kernel modes whose CTAs run their phases in lockstep (drt_render.cuh): bit 1 = the classed kernel
                                 * (measured +15 %: its hot code is 38 KB against a 32 KB instruction cache); bit 0 = the general kernel
-                                * (measured -26 % on stress_all: its phase-2 times differ too much between warps) */
+                                * (measured -26 % on stress_all: its phase-2 times differ too much between warps); bit 2 = the plastic-only kernel */
 #endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS

@@ -808,6 +808,18 @@ __device__ __forceinline__ uint32_t trace_path(const GeomT<R> &g, const SpdIndex
                     hdr16 = (uint32_t)DRT_CLASS_SPECULAR | (basis << 2) | (inside << 4) | ((uint32_t)sm << 5);
                 }
             }
+            if(nb == 0u)
+            {
+                /* every term of the path carries the first bounce's next-event or sampled-direction weights, so the vignette factor
+                 * (dot(ray direction, forward), sample_scene :612-615) is folded into them here, once per path by one thread, instead
+                 * of multiplying the finished spectrum in the replay (a path without a shaded bounce is scaled there) */
+                const float vig = rec[REC_VIG];
+                const uint32_t c = hdr16 & 3u;
+                recw[0] *= vig;
+                if(c != (uint32_t)DRT_CLASS_ROUGH) recw[1] *= vig;
+                if(c != (uint32_t)DRT_CLASS_SPECULAR) recw[2] *= vig;
+                if(c == (uint32_t)DRT_CLASS_PLASTIC) recw[3] *= vig;
+            }
             if(in_smem) reinterpret_cast<uint16_t *>(rec + REC_HDR16)[nb] = (uint16_t)hdr16;
             else reinterpret_cast<uint16_t *>(deep + L.deep_hdr_off)[nb - L.smem_depth] = (uint16_t)hdr16;
         }
@@ -1079,6 +1091,8 @@ __device__ __forceinline__ void replay_path(const float *col, const float *deep,
         const float4 *wp = reinterpret_cast<const float4 *>(col + L.head_words);
         const uint32_t nshade = nb & 0xffffu;
         {
+            /* every path starts with u = throughput * E = E (SpdIndex::light_pairs).  Loading E once per batch instead of once per
+             * path was measured: 5 more live registers spill in the 72-register kernel, -1.4 % */
             const unsigned long long *ep = reinterpret_cast<const unsigned long long *>(pool + ix.light_pairs) + lane16;
 #pragma unroll
             for(int k = 0; k < NP; k += 1) thr2[k] = ep[k * DRT_HALF];
@@ -1205,7 +1219,15 @@ __device__ __forceinline__ void replay_path(const float *col, const float *deep,
         }
     }
     }
-    const float vig = col[REC_VIG];
+    /* the vignette factor: compact records carry it in the first bounce's weights (trace_path) */
+    const float vig = (ALLFAST && (nb & 0xffffu) != 0u) ? 1.f : col[REC_VIG];
+    if(ALLFAST && (nb & 0xffffu) != 0u)
+    {
+#pragma unroll
+        for(int k = 0; k < NP; k += 1) upk2(dst2[k], c[2 * k], c[2 * k + 1]);
+        if(NS & 1) c[NS - 1] = dst1;
+        return;
+    }
     const unsigned long long vig2 = pk2(vig, vig);
 #pragma unroll
     for(int k = 0; k < NP; k += 1) upk2(mul2(dst2[k], vig2), c[2 * k], c[2 * k + 1]);
@@ -1359,7 +1381,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
     /* LOCKSTEP (a kernel whose hot code does not fit the 32 KB instruction cache; DRT_LOCKSTEP says which modes): the warps of a CTA
      * run their phases together -- a gate (an mbarrier that every warp arrives at once per phase and leaves for good when it runs
      * out of pixels) in front of phase 1 and of phase 2 -- so that at any time the SM fetches the code of ONE phase. */
-    constexpr bool LOCKSTEP = MODE == 2 ? ((DRT_LOCKSTEP & 2) != 0) : MODE == 0 ? ((DRT_LOCKSTEP & 1) != 0) : false;
+    constexpr bool LOCKSTEP = MODE == 2 ? ((DRT_LOCKSTEP & 2) != 0) : MODE == 0 ? ((DRT_LOCKSTEP & 1) != 0) : ((DRT_LOCKSTEP & 4) != 0);
     __shared__ unsigned long long phase_bar;
     const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&phase_bar);
     if(LOCKSTEP && threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(blockDim.x >> 5) : "memory");
