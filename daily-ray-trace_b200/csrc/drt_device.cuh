@@ -37,6 +37,9 @@
                                 * (measured +15 %: its hot code is 38 KB against a 32 KB instruction cache); bit 0 = the general kernel
                                 * (measured -26 % on stress_all: its phase-2 times differ too much between warps); bit 2 = the plastic-only kernel */
 #endif
+#ifndef DRT_GATE_SUSPEND_NS
+#define DRT_GATE_SUSPEND_NS 20000u   /* suspend-time hint of a phase gate's mbarrier.try_wait */
+#endif
 #define DRT_CTA_THREADS (DRT_CTA_WARPS * DRT_WARP)
 #ifndef DRT_MIN_CTAS
 #define DRT_MIN_CTAS 2        /* resident CTAs per SM the render kernels are compiled for (__launch_bounds__) */

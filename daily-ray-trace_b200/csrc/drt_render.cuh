@@ -949,6 +949,47 @@ static __device__ __noinline__ float fresnel_conductor_ab(float A, float B, floa
     return 0.5f * (par + per);
 }
 
+/* The same two Fresnel terms for TWO wavelength slots at once (packed f32x2 arithmetic; the square roots and reciprocals stay one
+ * MUFU per element): the classed kernel's specular and rough-conductor bounces evaluate them for the slot pairs (0,1), (2,3), ... */
+static __device__ __noinline__ unsigned long long fresnel_conductor_ab2(unsigned long long A2, unsigned long long B2, float inc_cos)
+{
+    const float cos_sq = inc_cos * inc_cos, sin_sq = 1.f - cos_sq;
+    const unsigned long long m1 = pk2(-1.f, -1.f), cs2 = pk2(cos_sq, cos_sq);
+    const unsigned long long r2 = add2(A2, pk2(-sin_sq, -sin_sq));
+    float q0, q1;
+    upk2(fma2(r2, r2, B2), q0, q1);
+    const unsigned long long apb2 = pk2(r_sqrt_fast(q0), r_sqrt_fast(q1));
+    upk2(mul2(add2(apb2, r2), pk2(0.5f, 0.5f)), q0, q1);
+    const unsigned long long a2 = pk2(r_sqrt_fast(fmaxf(q0, 0.f)), r_sqrt_fast(fmaxf(q1, 0.f)));   /* clamp: see fresnel_conductor_ab */
+    const unsigned long long s2 = add2(apb2, cs2);
+    const unsigned long long t2 = mul2(a2, pk2(2.f * inc_cos, 2.f * inc_cos));
+    const unsigned long long u2 = fma2(apb2, cs2, pk2(sin_sq * sin_sq, sin_sq * sin_sq));
+    const unsigned long long v2 = mul2(t2, pk2(sin_sq, sin_sq));
+    upk2(add2(s2, t2), q0, q1);
+    const unsigned long long par2 = mul2(fma2(t2, m1, s2), pk2(r_rcp_fast(q0), r_rcp_fast(q1)));
+    upk2(add2(u2, v2), q0, q1);
+    const unsigned long long per2 = mul2(mul2(par2, fma2(v2, m1, u2)), pk2(r_rcp_fast(q0), r_rcp_fast(q1)));
+    return mul2(add2(par2, per2), pk2(0.5f, 0.5f));
+}
+static __device__ __noinline__ unsigned long long fresnel_dielectric_rel2(unsigned long long rel2, float inc_cos)
+{
+    const float inc_sin_sq = 1.f - inc_cos * inc_cos;
+    const unsigned long long m1 = pk2(-1.f, -1.f), c2 = pk2(inc_cos, inc_cos);
+    const unsigned long long ts2 = mul2(mul2(rel2, rel2), pk2(inc_sin_sq, inc_sin_sq));
+    float t0, t1, q0, q1;
+    upk2(ts2, t0, t1);
+    upk2(fma2(mul2(ts2, m1), ts2, pk2(1.f, 1.f)), q0, q1);
+    const unsigned long long tc2 = pk2(r_sqrt_fast(fmaxf(q0, 0.f)), r_sqrt_fast(fmaxf(q1, 0.f)));   /* negative only under total reflection, replaced below */
+    const unsigned long long a2 = mul2(rel2, tc2), b2 = mul2(rel2, c2);
+    upk2(add2(c2, a2), q0, q1);
+    const unsigned long long par2 = mul2(fma2(a2, m1, c2), pk2(r_rcp_fast(q0), r_rcp_fast(q1)));
+    upk2(add2(b2, tc2), q0, q1);
+    const unsigned long long per2 = mul2(fma2(tc2, m1, b2), pk2(r_rcp_fast(q0), r_rcp_fast(q1)));
+    float f0, f1;
+    upk2(mul2(fma2(per2, per2, mul2(par2, par2)), pk2(0.5f, 0.5f)), f0, f1);
+    return pk2(t0 >= 1.f ? 1.f : f0, t1 >= 1.f ? 1.f : f1);   /* total internal reflection (bdsf.c:52) */
+}
+
 /* One BSDF evaluation expanded over this lane's wavelengths, any lobe list: the stored weights of the seven spectral bases
  * (eval_weights_general) times the bases.  `mask` is warp-uniform; a Fresnel basis whose weight is zero (every match-gated lobe under
  * next-event estimation) is not evaluated. */
@@ -975,7 +1016,13 @@ __device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint
     {
         const float *rel = pool_lane + ix.fres[surf_mat][inside][0];
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w_r, fresnel_dielectric_rel(rel[k * DRT_HALF], on_dot), f.v[k]);
+        for(int k = 0; k + 1 < NS; k += 2)
+        {
+            float r0, r1;
+            upk2(fresnel_dielectric_rel2(pk2(rel[k * DRT_HALF], rel[(k + 1) * DRT_HALF]), on_dot), r0, r1);
+            f.v[k] = fmaf(w_r, r0, f.v[k]); f.v[k + 1] = fmaf(w_r, r1, f.v[k + 1]);
+        }
+        if(NS & 1) f.v[NS - 1] = fmaf(w_r, fresnel_dielectric_rel(rel[(NS - 1) * DRT_HALF], on_dot), f.v[NS - 1]);
     }
     if(w_a != 0.f || w_b != 0.f)
     {
@@ -986,7 +1033,13 @@ __device__ __forceinline__ Spec<NS> eval_spectrum_general(const float *col, uint
             const float w = t ? w_b : w_a, cs = t ? c_b : on_dot;
             if(w == 0.f) continue;
 #pragma unroll
-            for(int k = 0; k < NS; k += 1) f.v[k] = fmaf(w, fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], cs), f.v[k]);
+            for(int k = 0; k + 1 < NS; k += 2)
+            {
+                float r0, r1;
+                upk2(fresnel_conductor_ab2(pk2(ra[k * DRT_HALF], ra[(k + 1) * DRT_HALF]), pk2(rb[k * DRT_HALF], rb[(k + 1) * DRT_HALF]), cs), r0, r1);
+                f.v[k] = fmaf(w, r0, f.v[k]); f.v[k + 1] = fmaf(w, r1, f.v[k + 1]);
+            }
+            if(NS & 1) f.v[NS - 1] = fmaf(w, fresnel_conductor_ab(ra[(NS - 1) * DRT_HALF], rb[(NS - 1) * DRT_HALF], cs), f.v[NS - 1]);
         }
     }
     return f;
@@ -1026,42 +1079,59 @@ static __device__ __noinline__ ShadeState<NS> shade_bounce_general(const float *
 }
 
 /* ------------------------------------------------------------------ classed kernel: specular and rough-conductor bounces */
-/* u = throughput * E and the radiance of a path, as the replay loop of the compact-record kernels carries them */
-template <int NS> struct Carry { float u[NS], d[NS]; };
-
-/* One bounce of class SPECULAR or ROUGH (record layout: RenderLaunch in drt_device.cuh), out of line: cold relative to the
- * plastic loop, and the Fresnel formulas exist once. */
+/* One bounce of class SPECULAR or ROUGH (record layout: RenderLaunch in drt_device.cuh) on the replay loop's packed state: u2 / u1 =
+ * throughput * E and d2 / d1 = radiance over the slot pairs and the odd last slot.  Inline (the struct-passing call cost 4 %), the
+ * Fresnel formulas themselves out of line. */
 template <int NS>
-static __device__ __noinline__ Carry<NS> shade_special(uint32_t hdr, float4 w, const float *pool_lane, const SpdIndex &ix, Carry<NS> st)
+__device__ __forceinline__ void shade_special(uint32_t hdr, float4 w, const float *pool_lane, const SpdIndex &ix,
+                                              unsigned long long (&u2)[NS / 2 > 0 ? NS / 2 : 1], unsigned long long (&d2)[NS / 2 > 0 ? NS / 2 : 1], float &u1, float &d1)
 {
+    constexpr int NP = NS / 2;
     const int cls = (int)(hdr & 3u), inside = (int)((hdr >> 4) & 1u), mat = (int)((hdr >> 5) & 31u);
     if(cls == DRT_CLASS_SPECULAR)
     {
+        /* throughput *= (c0 + c1 X) / pdf, cast_ray :467-469; X = mirror spectrum, dielectric R(on_dot) or conductor F(on_dot) */
         const uint32_t basis = (hdr >> 2) & 3u;
         const float *x0 = pool_lane + (basis == 0u ? ix.row[mat][DRT_SPD_MIRROR] : basis == 1u ? ix.fres[mat][inside][0] : ix.fres[mat][inside][1]);
         const float *x1 = pool_lane + ix.fres[mat][inside][2];
+        const unsigned long long c0 = pk2(w.x, w.x), c1 = pk2(w.y, w.y);
 #pragma unroll
-        for(int k = 0; k < NS; k += 1)
+        for(int k = 0; k < NP; k += 1)
         {
-            float x = x0[k * DRT_HALF];
+            unsigned long long x = pk2(x0[(2 * k) * DRT_HALF], x0[(2 * k + 1) * DRT_HALF]);
+            if(basis == 1u) x = fresnel_dielectric_rel2(x, w.z);
+            else if(basis == 2u) x = fresnel_conductor_ab2(x, pk2(x1[(2 * k) * DRT_HALF], x1[(2 * k + 1) * DRT_HALF]), w.z);
+            mul2_by(u2[k], fma2(c1, x, c0));
+        }
+        if(NS & 1)
+        {
+            float x = x0[(NS - 1) * DRT_HALF];
             if(basis == 1u) x = fresnel_dielectric_rel(x, w.z);
-            else if(basis == 2u) x = fresnel_conductor_ab(x, x1[k * DRT_HALF], w.z);
-            st.u[k] *= fmaf(w.y, x, w.x);   /* throughput *= (c0 + c1 X) / pdf, cast_ray :467-469 */
+            else if(basis == 2u) x = fresnel_conductor_ab(x, x1[(NS - 1) * DRT_HALF], w.z);
+            u1 *= fmaf(w.y, x, w.x);
         }
     }
     else
     {
         const float *ra = pool_lane + ix.fres[mat][inside][1], *rb = pool_lane + ix.fres[mat][inside][2];
+        /* the rows are re-read for the second evaluation: keeping them in registers across the calls spills */
+        auto rows2 = [&](int k, unsigned long long &a2, unsigned long long &b2)
+        {
+            a2 = pk2(ra[(2 * k) * DRT_HALF], ra[(2 * k + 1) * DRT_HALF]); b2 = pk2(rb[(2 * k) * DRT_HALF], rb[(2 * k + 1) * DRT_HALF]);
+        };
+        const float a1 = (NS & 1) ? ra[(NS - 1) * DRT_HALF] : 0.f, b1 = (NS & 1) ? rb[(NS - 1) * DRT_HALF] : 0.f;
         if(w.x != 0.f)   /* the light is visible: radiance += u * (w k F(cos_n)), :458-462 */
         {
+            const unsigned long long wn = pk2(w.x, w.x);
 #pragma unroll
-            for(int k = 0; k < NS; k += 1)
-                st.d[k] = fmaf(st.u[k], w.x * fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], w.y), st.d[k]);
+            for(int k = 0; k < NP; k += 1) { unsigned long long a2, b2; rows2(k, a2, b2); fma2_acc(d2[k], u2[k], mul2(wn, fresnel_conductor_ab2(a2, b2, w.y))); }
+            if(NS & 1) d1 = fmaf(u1, w.x * fresnel_conductor_ab(a1, b1, w.y), d1);
         }
+        const unsigned long long ws = pk2(w.z, w.z);
 #pragma unroll
-        for(int k = 0; k < NS; k += 1) st.u[k] *= w.z * fresnel_conductor_ab(ra[k * DRT_HALF], rb[k * DRT_HALF], w.w);
+        for(int k = 0; k < NP; k += 1) { unsigned long long a2, b2; rows2(k, a2, b2); mul2_by(u2[k], mul2(ws, fresnel_conductor_ab2(a2, b2, w.w))); }
+        if(NS & 1) u1 *= w.z * fresnel_conductor_ab(a1, b1, w.w);
     }
-    return st;
 }
 
 /* cast_ray's spectral arithmetic (daily_ray_trace.c:446-473) replayed from the record `col` (nb >= 1 bounces);
@@ -1113,14 +1183,7 @@ __device__ __forceinline__ void replay_path(const float *col, const float *deep,
             {
                 if(hdr & 3u)   /* a specular or rough-conductor bounce */
                 {
-                    Carry<NS> st;
-#pragma unroll
-                    for(int k = 0; k < NP; k += 1) { upk2(thr2[k], st.u[2 * k], st.u[2 * k + 1]); upk2(dst2[k], st.d[2 * k], st.d[2 * k + 1]); }
-                    if(NS & 1) { st.u[NS - 1] = thr1; st.d[NS - 1] = dst1; }
-                    st = shade_special<NS>(hdr, w, pool_lane, ix, st);
-#pragma unroll
-                    for(int k = 0; k < NP; k += 1) { thr2[k] = pk2(st.u[2 * k], st.u[2 * k + 1]); dst2[k] = pk2(st.d[2 * k], st.d[2 * k + 1]); }
-                    if(NS & 1) { thr1 = st.u[NS - 1]; dst1 = st.d[NS - 1]; }
+                    shade_special<NS>(hdr, w, pool_lane, ix, thr2, dst2, thr1, dst1);
                     hdr = hp[b + 1];
                     w = wp[b + 1];
                     continue;
@@ -1457,10 +1520,12 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
         {
             if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
             __syncwarp();
+            /* try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+             * spinning -- a spinning gate took 27 % of the kernel's issued instructions (profiles/r2_ncu_classed_kernel.md) */
             uint32_t ok = 0;
             while(!ok)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(ok) : "r"(bar_addr), "r"(gate_parity) : "memory");
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(bar_addr), "r"(gate_parity), "r"(DRT_GATE_SUSPEND_NS) : "memory");
             gate_parity ^= 1u;
         }
     };
