@@ -1,0 +1,10 @@
+#!/bin/bash
+# The round's multi-GPU measurement session on one 8-GPU box: north-star strong scaling at N = 8, 4, 2; configs[4] in full; configs[2] sweep.
+S="--steps 5 --warmup 3"
+tools/run_scaling.sh r2_n8 8 $S
+tools/run_scaling.sh r2_n4 4 $S --no-cpu-baseline
+tools/run_scaling.sh r2_n2 2 $S --no-cpu-baseline
+# configs[4]: cornell_large_box 4096x4096 at 4096 spp on 8 GPUs (512 per GPU), film 13.9 GB in all, sharded over the owners
+timeout 400 tools/run_scaling.sh r2_n8_cornell_large_box_4096x4096_4096spp 8 --scene cornell_large_box --width 4096 --height 4096 --spp 4096 --steps 2 --warmup 1 --no-other-scaling
+# configs[2]: cornell_plane_light 1024x1024 sample-count sweep at 2, 4, 8 GPUs (N = 1 is measured on the single-GPU box)
+for n in 8 4 2; do timeout 300 tools/run_scaling.sh r2_n${n}_cornell_plane_light_sweep $n --scene cornell_plane_light --spp 1024 $S --no-cpu-baseline --spp-sweep 1,4,16,64,256,1024; done
