@@ -1,6 +1,6 @@
 /*
- * csrc/drt_render.cuh -- the render hot path as one persistent sm_100a kernel (a template; instantiated by
- * drt_kernels_fast.cu, drt_kernels_general.cu and drt_kernels_f64.cu, dispatched by drt_kernels.cu).
+ * csrc/drt_render.cuh -- the render hot path as one persistent sm_100a kernel (a template; instantiated by the
+ * drt_kernels_{fast,classed,general,f64}[_deep].cu translation units, dispatched by drt_kernels.cu).
  *
  * What the reference does per camera path (sample_scene -> cast_ray -> ..., src/daily_ray_trace.c:432-618) is split
  * along the one axis that never feeds back: NOTHING geometric depends on wavelength (refraction uses n(630 nm) only,
@@ -16,12 +16,19 @@
  *                     and the pixel's film (sum, Welford mean and M2, daily_ray_trace.c:732-743) stays in registers
  *                     for ALL samples of the pixel: each film plane is written to HBM exactly once, coalesced (K6).
  *
- * No path state ever goes to global memory; HBM traffic is the film write, so the kernel is bound by FP32 issue, not
- * by the 1.2 KB-per-bounce queue traffic of a global-memory wavefront.
+ * No path state goes to global memory (deep renders excepted, see DEEP); HBM traffic is the film write, so the kernel is bound by
+ * FP32 issue, not by the 1.2 KB-per-bounce queue traffic of a global-memory wavefront.
  *
- * Template parameters: R = float (default) or double (branch-flip diagnostic) arithmetic of phase 1; NS = wavelength slots
- * per half-warp lane (2, 3, 5, 8); ALLFAST = every surface material is a two-lobe plastic under one light (compact records,
- * no general evaluators, 72 registers -> 2 CTAs x 14 warps per SM); PAIRED = one pixel per task (spp >= 32) or 32/spp pixels.
+ * Template parameters: R = float (default) or double (branch-flip diagnostic) arithmetic of phase 1; NS = wavelength slots per
+ * half-warp lane (2, 3, 5, 8); PAIRED = one pixel per task (spp >= 32) or 32/spp pixels; MODE, chosen at scene upload:
+ *   1 plastic-only  every surface material is a bp_diffuse / bp_glossy plastic under ONE light that is the scene's only emitter:
+ *                   compact 4-word bounce records, the replay carries u = throughput * E; 72 registers, 2 CTAs x 14 warps per SM
+ *   2 classed       the same records for plastics, single-basis specular materials (mirror, fs_conductor, glass R / T) and
+ *                   ct_conductor (GeomT::mclass); its hot code exceeds the 32 KB instruction cache, so the warps of a CTA run their
+ *                   phases in lockstep behind mbarrier gates (LOCKSTEP); 64 registers, 2 CTAs x 16 warps
+ *   0 general       any lobe list, any sampler, any number of lights, emissive escape material: general records, 2 CTAs x 8 warps
+ * DEEP = the instantiation for renders whose records do not fit in shared memory at full occupancy: bounces past
+ * RenderLaunch::smem_depth overflow to per-slot rows in global memory (L2-resident), so max_cast_depth x lights is unbounded.
  * Work the kernel proves unnecessary on the host's word (drt_capi.cu, exact): shadow rays do not test boundary planes
  * (GeomT::nax_b), pixels outside the scene's screen-space bound are counted instead of traced (RenderLaunch::hit_*).
  * Quirk numbers (Qn) refer to SURVEY.md Appendix A; the CPU restatement of the same lines is oracle/drt_oracle.c.
@@ -1446,8 +1453,13 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
      * out of pixels) in front of phase 1 and of phase 2 -- so that at any time the SM fetches the code of ONE phase. */
     constexpr bool LOCKSTEP = MODE == 2 ? ((DRT_LOCKSTEP & 2) != 0) : MODE == 0 ? ((DRT_LOCKSTEP & 1) != 0) : ((DRT_LOCKSTEP & 4) != 0);
     __shared__ unsigned long long phase_bar;
+    __shared__ uint32_t gates_off;
     const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&phase_bar);
-    if(LOCKSTEP && threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(blockDim.x >> 5) : "memory");
+    if(LOCKSTEP && threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(blockDim.x >> 5) : "memory");
+        gates_off = L.scatter_count > 1 ? 1u : 0u;   /* see DRT_GATE_PATIENCE in drt_device.cuh */
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
     size_t off = (sizeof(GeomT<R>) + 15) & ~size_t(15);
@@ -1518,14 +1530,25 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
     {
         if constexpr(LOCKSTEP)
         {
+            /* The gates only steer WHEN the warps of a CTA run their phases (one phase's code in the instruction cache at a time); no
+             * data passes through them.  So they are allowed to fail safe: a warp that has waited DRT_GATE_PATIENCE hints (about 10 ms,
+             * two orders above a phase) switches the CTA's gates off for the rest of the launch instead of waiting on. */
+            if(*reinterpret_cast<volatile uint32_t *>(&gates_off)) return;
             if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
             __syncwarp();
             /* try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
              * spinning -- a spinning gate took 27 % of the kernel's issued instructions (profiles/r2_ncu_classed_kernel.md) */
-            uint32_t ok = 0;
+            uint32_t ok = 0, spins = 0;
             while(!ok)
+            {
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                              : "=r"(ok) : "r"(bar_addr), "r"(gate_parity), "r"(DRT_GATE_SUSPEND_NS) : "memory");
+                if(!ok && (++spins > DRT_GATE_PATIENCE || *reinterpret_cast<volatile uint32_t *>(&gates_off)))
+                {
+                    gates_off = 1u;
+                    break;
+                }
+            }
             gate_parity ^= 1u;
         }
     };

@@ -79,3 +79,33 @@ def test_linux_main_on_several_gpus(host, tmp_path, gpus):
     for a, b in ((many_sum[:, :n], one_sum[:, :n]), (many_mean, one_mean)):
         floor = 1e-5 * np.abs(b).max()
         assert (np.abs(a - b) / np.maximum(np.abs(b), floor)).max() < 2e-4
+
+
+def test_more_devices_than_samples(host, tmp_path):
+    """`--gpus 2` with ONE sample per pixel: the samples cannot be split, the surplus device idles (drt_cuda_render_host_multi falls back
+    to the devices that have work) and the films equal the single-device run bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = refdriver.make_root(str(tmp_path), common.ASSETS)
+    w, h, n = 24, 16, 69
+    open(os.path.join(root, "config.cfg"), "w").write(host.make_config_text(scene="scenes\\cornell_plane_light.scn", width=w, height=h, spp=1))
+
+    def run(args):
+        subprocess.run([BIN, "--seed", "5"] + args, cwd=root, check=True, capture_output=True, text=True)
+        return {k: open(os.path.join(root, "output", k), "rb").read() for k in ("output.spd", "average.spd", "output.bmp")}
+
+    assert run([]) == run(["--gpus", "2"])
+
+
+@pytest.mark.parametrize("spp,depth", [(0, 4), (3, 0)])
+def test_main_with_no_samples_or_no_depth(host, tmp_path, spp, depth):
+    """num_pixel_samples 0 / max_cast_depth 0 are valid configurations of the reference (its loops simply do not run): black films,
+    filter = sample count, not an error."""
+    root = refdriver.make_root(str(tmp_path), common.ASSETS)
+    w, h, n = 16, 12, 69
+    open(os.path.join(root, "config.cfg"), "w").write(host.make_config_text(scene="scenes\\cornell_plane_light.scn", width=w, height=h, spp=spp, depth=depth))
+    out = subprocess.run([BIN], cwd=root, check=True, capture_output=True, text=True).stdout
+    assert "Render complete." in out
+    body = np.frombuffer(open(os.path.join(root, "output", "output.spd"), "rb").read()[40:], dtype=np.float64).reshape(w * h, n + 1)
+    assert not body[:, :n].any() and (body[:, n] == spp).all()
