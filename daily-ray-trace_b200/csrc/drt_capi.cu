@@ -222,6 +222,47 @@ static int classify_material(const drt_scene *s, int m, int *nd_out, int *ng_out
     return DRT_CLASS_GENERAL;
 }
 
+/* Which render kernel a scene gets (drt_render.cuh): 1 plastic-only, 2 classed, 0 general. */
+static int scene_kernel_mode(const drt_scene *scene)
+{
+    int nlights = 0;
+    for(int i = 0; i < scene->num_surfaces; i += 1) nlights += scene->materials[scene->surfaces[i].material].is_emissive ? 1 : 0;
+    bool all_fast = nlights == 1 && !scene->materials[scene->escape_material].is_emissive, classed = all_fast;
+    for(int i = 0; i < scene->num_surfaces; i += 1)
+    {
+        const int m = scene->surfaces[i].material;
+        if(scene->materials[m].is_black_body || scene->surfaces[i].type == DRT_GEO_POINT || scene->surfaces[i].type == DRT_GEO_NONE) continue;
+        const int cls = classify_material(scene, m, nullptr, nullptr, nullptr);
+        if(cls != DRT_CLASS_PLASTIC) all_fast = false;
+        if(cls == DRT_CLASS_GENERAL) classed = false;
+    }
+    if(getenv("DRT_NO_CLASSED")) classed = all_fast;   /* A/B switch: mixed scenes on the general kernel */
+    return all_fast ? 1 : classed ? 2 : 0;
+}
+
+template <typename R>
+static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c);
+
+extern "C" int drt_cuda_plan_scene(const drt_scene *scene, const drt_camera *camera, int32_t *kernel_mode_out, int32_t *material_class, float *specular_constants)
+{
+    if(!scene || !camera || !kernel_mode_out) return fail(DRT_CUDA_E_ARG, "NULL argument");
+    int rc = drt_cuda_validate_scene(scene);
+    if(rc != DRT_CUDA_OK) return rc;
+    *kernel_mode_out = scene_kernel_mode(scene);
+    if(material_class || specular_constants)
+    {
+        GeomT<float> *g = new GeomT<float>();
+        fill_geom(g, scene, camera);
+        for(int m = 0; m < scene->num_materials; m += 1)
+        {
+            if(material_class) material_class[m] = g->mclass[m];
+            if(specular_constants) memcpy(specular_constants + (size_t)m * 6, g->spec_c[m], 6 * sizeof(float));
+        }
+        delete g;
+    }
+    return DRT_CUDA_OK;
+}
+
 template <typename R>
 static void fill_geom(GeomT<R> *g, const drt_scene *s, const drt_camera *c)
 {
@@ -583,16 +624,8 @@ extern "C" int drt_cuda_upload_scene(drt_cuda_context *ctx, const drt_scene *sce
     /* The compact-record kernels carry throughput * E(light): the only emitter a path can run into must then be that light, so an
      * emissive escape material (a sky, Q19) or a second light sends the scene to the general kernel.  all_fast: every surface
      * material is a plastic (kernel mode 1); classed: plastics, single-basis specular materials and ct_conductor (mode 2). */
-    bool all_fast = nlights == 1 && !scene->materials[scene->escape_material].is_emissive, classed = all_fast;
-    for(int i = 0; i < scene->num_surfaces; i += 1)
-    {
-        const int m = scene->surfaces[i].material;
-        if(scene->materials[m].is_black_body || scene->surfaces[i].type == DRT_GEO_POINT || scene->surfaces[i].type == DRT_GEO_NONE) continue;
-        const int cls = classify_material(scene, m, nullptr, nullptr, nullptr);
-        if(cls != DRT_CLASS_PLASTIC) all_fast = false;
-        if(cls == DRT_CLASS_GENERAL) classed = false;
-    }
-    if(getenv("DRT_NO_CLASSED")) classed = all_fast;   /* A/B switch: mixed scenes on the general kernel */
+    int mode = scene_kernel_mode(scene);
+    bool all_fast = mode == 1, classed = mode != 0;
     if(pool.size() > 65535) all_fast = classed = false;   /* compact records address the blocks with 16-bit word offsets */
     int eval_words = g32->eval_words > 0 ? g32->eval_words : 1;
     delete g32; delete g64;

@@ -19,7 +19,7 @@ EXPORTS = ["drt_cuda_last_error", "drt_cuda_device_count", "drt_cuda_create", "d
            "drt_cuda_film_ipc_open", "drt_cuda_film_ipc_close", "drt_cuda_film_merge_many", "drt_cuda_film_merge_slices", "drt_cuda_render_device_scatter", "drt_cuda_debug_records", "drt_cuda_buffer_alloc", "drt_cuda_buffer_free",
            "drt_cuda_buffer_ipc_export", "drt_cuda_buffer_ipc_open", "drt_cuda_buffer_ipc_close",
            "drt_cuda_film_merge_slices_local", "drt_cuda_film_read_slice", "drt_cuda_flags_signal", "drt_cuda_flags_wait", "drt_cuda_flags_timeouts",
-           "drt_cuda_host_alloc", "drt_cuda_host_free", "drt_cuda_render_host_multi_images", "drt_cuda_render_device_scatter_band"]
+           "drt_cuda_host_alloc", "drt_cuda_host_free", "drt_cuda_render_host_multi_images", "drt_cuda_render_device_scatter_band", "drt_cuda_plan_scene"]
 
 
 class Film(C.Structure):
@@ -61,6 +61,7 @@ def lib():
         L.drt_cuda_upload_scene.argtypes = [C.c_void_p, C.POINTER(Scene), C.POINTER(Camera), C.POINTER(Tables)]
         L.drt_cuda_scene_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.drt_cuda_validate_scene.argtypes = [C.POINTER(Scene)]
+        L.drt_cuda_plan_scene.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.drt_cuda_analyse_scene.argtypes = [C.POINTER(Scene), C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32 * 4), C.POINTER(C.c_int32)]
         L.drt_cuda_render_kernel_info.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.drt_cuda_set_geometry_precision.argtypes = [C.c_void_p, C.c_int]
@@ -296,6 +297,15 @@ def render_host_multi(contexts, params):
 def validate_scene(scene):
     """Raises CudaError for a scene drt_cuda_upload_scene would reject (host arithmetic, no device needed)."""
     _check(lib().drt_cuda_validate_scene(C.byref(scene)))
+
+
+def plan_scene(scene, camera):
+    """(kernel mode, class per material, specular constants [materials][3][2]) of drt_cuda_plan_scene: host arithmetic, no device needed."""
+    mode = C.c_int32()
+    classes = (C.c_int32 * scene.num_materials)()
+    consts = (C.c_float * (scene.num_materials * 6))()
+    _check(lib().drt_cuda_plan_scene(C.byref(scene), C.byref(camera), C.byref(mode), classes, consts))
+    return mode.value, list(classes), np.array(consts, dtype=np.float32).reshape(scene.num_materials, 3, 2)
 
 
 def analyse_scene(scene, camera, width, height):

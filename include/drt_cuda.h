@@ -131,6 +131,14 @@ int  drt_cuda_render_kernel_info(drt_cuda_context *ctx, const drt_render_params 
 int  drt_cuda_analyse_scene(const drt_scene *scene, const drt_camera *camera, uint32_t width, uint32_t height,
                             uint32_t hit_rect[4], int32_t *boundary /* [scene->num_surfaces] */);
 
+/* What drt_cuda_upload_scene decides about a scene, as plain host arithmetic (no device needed; used by the CPU-tier tests):
+ * *kernel_mode = 1 plastic-only, 2 classed, 0 general (csrc/drt_render.cuh; f64 geometry always runs the general kernel);
+ * material_class[m] (may be NULL) = 0 plastic, 1 single-basis specular, 2 rough conductor, 3 general, for every material;
+ * specular_constants[m][match][2] (may be NULL; match 0 none, 1 reflection, 2 refraction) = the constants (c0, c1) of the
+ * bdsf() sum c0 + c1 X of a specular material, tabulated by walking its lobe list with the reference's stale-scratch rule (Q7). */
+int  drt_cuda_plan_scene(const drt_scene *scene, const drt_camera *camera, int32_t *kernel_mode,
+                         int32_t *material_class /* [scene->num_materials] */, float *specular_constants /* [scene->num_materials][3][2] */);
+
 /* Counters of the most recent render_* / sample_paths call (waits for it to finish). */
 int  drt_cuda_get_stats(drt_cuda_context *ctx, drt_cuda_stats *out);
 

@@ -158,3 +158,66 @@ def test_slice_partition_covers_every_pixel_once(npix, world):
         assert 0 <= p0 <= p1 <= npix and p1 - p0 <= per
         covered[p0:p1] += 1
     assert (covered == 1).all()
+
+
+@pytest.mark.parametrize("npix,world", [(1024 * 1024, 8), (37 * 23, 3), (64 * 33, 8), (4096 * 4096, 8), (640 * 480, 6), (100, 2)])
+def test_bands_of_the_scattered_render_cover_every_pixel_once(npix, world):
+    """The banded exchange renders, per band, the same part [b0, b1) of EVERY owner's slice: task t of a band is pixel
+    (t / chunk) * slice + b0 + t % chunk, tasks past the end of the image are empty (render_kernel, RenderLaunch::band_*).  This is
+    that arithmetic in numpy with the band boundaries of film.ShardedFilmGroup / drt_cuda_render_host_multi: over all bands every
+    pixel is rendered exactly once, and every owner merges exactly its own pixels."""
+    slice_px, parts = film.slice_partition(npix, world)
+    cuts = film.ShardedFilmGroup.BAND_CUTS
+    rendered = np.zeros(npix, np.int32)
+    merged = np.zeros(npix, np.int32)
+    for b in range(len(cuts) - 1):
+        b0, b1 = slice_px * cuts[b] // 16, slice_px * cuts[b + 1] // 16
+        if b1 <= b0:
+            continue
+        chunk = b1 - b0
+        t = np.arange(chunk * world, dtype=np.int64)                      # the band's tasks, as the kernel maps them
+        pix = (t // chunk) * slice_px + b0 + t % chunk
+        pix = pix[pix < npix]
+        np.add.at(rendered, pix, 1)
+        for r, (p0, p1) in enumerate(parts):                              # what owner r merges and reads back for this band
+            q0, q1 = min(p1, p0 + b0), min(p1, p0 + b1)
+            merged[q0:q1] += 1
+            assert q0 >= p0 and q1 <= p1
+    assert (rendered == 1).all() and (merged == 1).all()
+
+
+@pytest.mark.parametrize("name,mode", [("init_cornell", 1), ("cornell_large_box", 1), ("cornell_downward", 2), ("first_scene", 1), ("example_scene", 1),
+                                       ("rotated_room", 1), ("plane_light_all_plastic", 1), ("cornell_plane_light", 2), ("classed_all", 2),
+                                       ("stress_all", 0), ("sky_cornell", 0)])
+def test_kernel_mode_of_every_scene(name, mode):
+    """Which render kernel a scene gets (drt_cuda_plan_scene, the decision drt_cuda_upload_scene takes; host arithmetic): plastic-only
+    (1) for plastics under one light, classed (2) when specular / rough-conductor materials join them, general (0) for several lights,
+    an emissive escape material or other lobe lists."""
+    cfg, tables, scene, camera = common.load(name, 32, 32, 1, 4)
+    got, classes, _ = cuda.plan_scene(scene, camera)
+    assert got == mode, (name, got, classes)
+
+
+def test_material_classes_and_specular_constants():
+    """classed_all holds every class.  The constants (c0, c1) of a specular material's bdsf() sum c0 + c1 X follow from walking its lobe
+    list the way bdsf() does (daily_ray_trace.c:215-229): a lobe that does not write leaves the previous lobe's value in the scratch
+    spectrum, which is added AGAIN (Q7) -- so glass [R, T] gives 2 R under reflection and 1 - R under refraction."""
+    cfg, tables, scene, camera = common.load("classed_all", 32, 32, 1, 4)
+    mode, classes, consts = cuda.plan_scene(scene, camera)
+    by_name = {scene.materials[m].name.decode(): m for m in range(scene.num_materials)}
+    PLASTIC, SPECULAR, ROUGH = 0, 1, 2
+    for nm in ("grey", "red", "sheen", "thick"):
+        assert classes[by_name[nm]] == PLASTIC, nm
+    for nm in ("chrome", "mirror", "glass", "clear"):
+        assert classes[by_name[nm]] == SPECULAR, nm
+    assert classes[by_name["rough_gold"]] == ROUGH
+    none, refl, refr = 0, 1, 2
+    assert consts[by_name["glass"]].tolist() == [[0, 0], [0, 2], [1, -1]]          # R then stale R again; 0 then 1 - R
+    assert consts[by_name["clear"]].tolist() == [[0, 0], [0, 0], [1, -1]]          # transmittance only
+    assert consts[by_name["mirror"]].tolist() == [[0, 0], [0, 1], [0, 0]]          # mirror_bdsf writes zero on a mismatch
+    assert consts[by_name["chrome"]].tolist() == [[0, 0], [0, 1], [0, 0]]
+    # stress_all's stale_mix = [bp_diffuse, fs_dielectric_reflectance, bp_diffuse] mixes a plastic lobe with a gated one: general
+    cfg, tables, scene, camera = common.load("stress_all", 32, 32, 1, 4)
+    mode, classes, _ = cuda.plan_scene(scene, camera)
+    by_name = {scene.materials[m].name.decode(): m for m in range(scene.num_materials)}
+    assert mode == 0 and classes[by_name["stale_mix"]] == 3
