@@ -37,13 +37,13 @@
                                 * (measured +15 %: its hot code is 38 KB against a 32 KB instruction cache); bit 0 = the general kernel
                                 * (measured -26 % on stress_all: its phase-2 times differ too much between warps); bit 2 = the plastic-only kernel */
 #endif
-#ifndef DRT_GATE_PATIENCE
-/* A phase gate gives up after this many expired suspend hints (500 x 20 us = 10 ms; a phase takes 50 - 200 us) and switches the
+#ifndef DRT_GATE_PATIENCE_CYCLES
+/* A phase gate gives up after this many SM clock cycles (about 10 ms at 1.97 GHz; a phase takes 50 - 200 us) and switches the
  * CTA's gates off: lockstep is a performance aid, never a dependency.  Multi-GPU renders (scatter_count > 1) start with the gates
  * off: bench.py --scene cornell_plane_light --gpus 2/4/8 did not complete in the round's last GPU session (cause not found before
  * the GPU budget ran out; the same kernel passes every single-device and in-process two-device test), and an untested multi-rank
  * combination is not worth 13 % -- see DESIGN.md section 9. */
-#define DRT_GATE_PATIENCE 500u
+#define DRT_GATE_PATIENCE_CYCLES 20000000ll
 #endif
 #ifndef DRT_GATE_SUSPEND_NS
 #define DRT_GATE_SUSPEND_NS 20000u   /* suspend-time hint of a phase gate's mbarrier.try_wait */

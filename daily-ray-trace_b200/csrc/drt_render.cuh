@@ -1458,7 +1458,7 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
     if(LOCKSTEP && threadIdx.x == 0)
     {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(blockDim.x >> 5) : "memory");
-        gates_off = L.scatter_count > 1 ? 1u : 0u;   /* see DRT_GATE_PATIENCE in drt_device.cuh */
+        gates_off = L.scatter_count > 1 ? 1u : 0u;   /* see DRT_GATE_PATIENCE_CYCLES in drt_device.cuh */
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GeomT<R> *sg = reinterpret_cast<GeomT<R> *>(smem_raw);
@@ -1531,19 +1531,20 @@ __global__ void __launch_bounds__((MODE == 1 ? DRT_FAST_WARPS : MODE == 2 ? DRT_
         if constexpr(LOCKSTEP)
         {
             /* The gates only steer WHEN the warps of a CTA run their phases (one phase's code in the instruction cache at a time); no
-             * data passes through them.  So they are allowed to fail safe: a warp that has waited DRT_GATE_PATIENCE hints (about 10 ms,
+             * data passes through them.  So they are allowed to fail safe: a warp that has waited DRT_GATE_PATIENCE_CYCLES (about 10 ms,
              * two orders above a phase) switches the CTA's gates off for the rest of the launch instead of waiting on. */
             if(*reinterpret_cast<volatile uint32_t *>(&gates_off)) return;
             if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar_addr) : "memory");
             __syncwarp();
             /* try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
              * spinning -- a spinning gate took 27 % of the kernel's issued instructions (profiles/r2_ncu_classed_kernel.md) */
-            uint32_t ok = 0, spins = 0;
+            uint32_t ok = 0;
+            const long long t0 = clock64();
             while(!ok)
             {
                 asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                              : "=r"(ok) : "r"(bar_addr), "r"(gate_parity), "r"(DRT_GATE_SUSPEND_NS) : "memory");
-                if(!ok && (++spins > DRT_GATE_PATIENCE || *reinterpret_cast<volatile uint32_t *>(&gates_off)))
+                if(!ok && (clock64() - t0 > DRT_GATE_PATIENCE_CYCLES || *reinterpret_cast<volatile uint32_t *>(&gates_off)))
                 {
                     gates_off = 1u;
                     break;
