@@ -6,5 +6,7 @@ tools/run_scaling.sh r2_n4 4 $S --no-cpu-baseline
 tools/run_scaling.sh r2_n2 2 $S --no-cpu-baseline
 # configs[4]: cornell_large_box 4096x4096 at 4096 spp on 8 GPUs (512 per GPU), film 13.9 GB in all, sharded over the owners
 timeout 400 tools/run_scaling.sh r2_n8_cornell_large_box_4096x4096_4096spp 8 --scene cornell_large_box --width 4096 --height 4096 --spp 4096 --steps 2 --warmup 1 --no-other-scaling
-# configs[2]: cornell_plane_light 1024x1024 sample-count sweep at 2, 4, 8 GPUs (N = 1 is measured on the single-GPU box)
+# configs[2]: cornell_plane_light 1024x1024 sample-count sweep at 2, 4, 8 GPUs (N = 1 is measured on the single-GPU box).
+# NOTE (round 2): these three runs printed nothing within their 300 s and used up the round's GPU budget;
+# run ONE of them alone, with a short timeout, before repeating the session.
 for n in 8 4 2; do timeout 300 tools/run_scaling.sh r2_n${n}_cornell_plane_light_sweep $n --scene cornell_plane_light --spp 1024 $S --no-cpu-baseline --spp-sweep 1,4,16,64,256,1024; done
