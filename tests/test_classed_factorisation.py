@@ -146,3 +146,32 @@ def test_rough_conductor_is_w_times_f_of_the_half_vector(loaded):
         got = w * conductor_ab(eta * eta - kap * kap, 4.0 * eta * eta * kap * kap, abs(d))
         want = ref.bdsf(m, base, m, nrm, out, inn)
         assert np.allclose(got, want, rtol=1e-9, atol=1e-12), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("material,nd,ng", [("grey", 1, 1), ("red", 1, 0), ("sheen", 0, 2), ("thick", 2, 1)])
+def test_plastics_are_lobe_multiplicities_times_two_weights(loaded, material, nd, ng):
+    """A plastic's bdsf() sum is nd * w_d * D + ng * w_g * G (both lobes always write, so a lobe listed k times counts k times,
+    daily_ray_trace.c:215-229): the multiplicities live in the material's D, G block (SpdIndex::plastic2), the kernel computes the two
+    weights w_d = |n.in| / pi and w_g = max(0, n.h)^shininess |n.in| (bdsf.c:105-119)."""
+    ref, scene, classes, consts, names = loaded
+    m, base = names[material], scene.base_material
+    assert classes[m] == 0
+    n = scene.num_wavelengths
+    mat = scene.materials[m]
+    lobes = list(mat.lobes[:mat.num_lobes])
+    assert (lobes.count(0), lobes.count(1)) == (nd, ng)
+    D = np.array(mat.spd[DIFFUSE][:n]) if mat.spd_mask & (1 << DIFFUSE) else np.zeros(n)
+    G = np.array(mat.spd[GLOSSY][:n]) if mat.spd_mask & (1 << GLOSSY) else np.zeros(n)
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        nrm = rng.normal(size=3); nrm /= np.sqrt(dot(nrm, nrm))
+        out = rng.normal(size=3); out /= np.sqrt(dot(out, out))
+        inn = rng.normal(size=3); inn /= np.sqrt(dot(inn, inn))
+        if dot(nrm, out) < 0: out = -out
+        h = out + inn; h /= np.sqrt(dot(h, h))
+        cos_in = abs(dot(nrm, inn))
+        w_d = cos_in / np.pi
+        w_g = max(0.0, dot(nrm, h)) ** mat.shininess * cos_in
+        got = nd * w_d * D + ng * w_g * G
+        want = ref.bdsf(m, base, m, nrm, out, inn)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-15), (material, np.abs(got - want).max())
